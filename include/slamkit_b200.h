@@ -1,0 +1,151 @@
+/* slamkit_b200 -- C ABI of the B200-native hot paths of slp-rl/slamkit.
+ *
+ * The reference has no native code and no FFI of its own: both hot paths enter third-party
+ * Python libraries through two plugin ABCs.  This header is therefore the interface a binding for those two plugin
+ * points would use; each entry point cites the reference call site it replaces (paths relative to the reference
+ * repo; "HF:" = transformers 5.5.0, "SK:" = scikit-learn 1.9.0).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is caller-owned DEVICE memory unless the name ends in _host;
+ *   - no allocation and no synchronisation inside compute calls: work is enqueued on `stream` (a cudaStream_t passed
+ *     as void*) and ordered with the caller's other work on that stream;
+ *   - return 0 on success, <0 on error (-1 bad argument, -2 CUDA error); sk_last_error() returns a message;
+ *   - bf16 tensors are passed as void* (uint16 storage), row-major, with explicit leading dimensions (in elements);
+ *   - handles are re-entrant per handle, not thread-safe across threads sharing one handle.
+ */
+#ifndef SLAMKIT_B200_H
+#define SLAMKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+const char* sk_last_error(void);
+int sk_version(void);                       /* 100*major + minor */
+int sk_device_sm_count(void);               /* multiprocessor count of the current device (148 on B200) */
+int sk_device_cc(void);                     /* 10*major + minor of the current device; kernels require 100 */
+
+/* ---- tensor-core GEMM (tcgen05 + TMA + TMEM) ------------------------------------------------------------------
+ * C[M,N] = A * B^T (+ bias[N]) (+ residual[M,N]); bf16 operands, fp32 accumulation, bf16 (or fp32) output.
+ *   a_mn = 0: A is [M,K] row-major (lda = row pitch);  a_mn = 1: A is stored transposed as [K,M] (lda = its pitch).
+ *   b_mn = 0: B is [N,K] row-major (a torch Linear weight);  b_mn = 1: B is stored as [K,N].
+ *   act: 0 none, 1 GELU(erf) on (acc+bias).  round_before_res: round (acc+bias) to bf16 before adding the residual
+ *   (bit-matches an unfused bf16 linear followed by a bf16 add).  force_bn: 0 auto, else 64/128/256.
+ * Replaces every torch.nn.Linear / F.linear on both hot paths (HF:models/qwen2/modeling_qwen2.py:35-48,187-246;
+ * HF:models/hubert/modeling_hubert.py:216-231,262-405) and their autograd dgrad/wgrad GEMMs. */
+int sk_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                 int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
+                 int force_bn, void* stream);
+
+/* ---- causal-LM element-wise / reduction kernels (path (ii)) --------------------------------------------------- */
+/* Embedding lookup, HF:models/qwen2/modeling_qwen2.py:332-415 (embed_tokens). ids int64 [M]. */
+int sk_embed_fwd(const int64_t* ids, const void* table, void* out, int M, int D, int V, void* stream);
+/* dTable[ids[m]] += dx[m]; scratch: fp32 [Vpad*D]; accumulate=1 keeps the existing bf16 gradient. */
+int sk_embed_bwd(const int64_t* ids, const void* dx, float* scratch, void* dtable, int M, int D, int V, int Vpad,
+                 int accumulate, void* stream);
+/* Qwen2RMSNorm, HF:models/qwen2/modeling_qwen2.py:249-262. rstd (fp32 [M]) may be NULL. */
+int sk_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int D, float eps, void* stream);
+/* dx = d(rmsnorm)(dy) (+ dres);  dw (+)= sum_rows dy*xhat.  dw_partial: fp32 [sk_rmsnorm_bwd_blocks()*D]. */
+int sk_rmsnorm_bwd_blocks(void);
+int sk_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                   void* dw, float* dw_partial, int M, int D, int accumulate_dw, void* stream);
+/* Column sums of a bf16 matrix (bias gradient). partial: fp32 [sk_colsum_splits()*N]. */
+int sk_colsum_splits(void);
+int sk_colsum(const void* x, void* out, float* partial, int M, int N, int ld, int accumulate, void* stream);
+/* Rotary embedding (rotate_half form) in place on the first n_rot_heads heads of each row,
+ * HF:models/qwen2/modeling_qwen2.py:102-146 (apply_rotary_pos_emb). cos/sin: bf16 [maxpos, head_dim/2].
+ * pos_ids: int32 [M] or NULL (position = row % T). inverse=1 applies the transposed rotation (backward). */
+int sk_rope(void* qkv, const void* cos_t, const void* sin_t, const int32_t* pos_ids, int M, int T, int ld,
+            int n_rot_heads, int head_dim, int inverse, void* stream);
+/* Qwen2MLP activation down(silu(gate)*up), HF:models/qwen2/modeling_qwen2.py:35-48. gu = [gate | up], each F wide. */
+int sk_swiglu_fwd(const void* gu, void* act, int M, int F, void* stream);
+int sk_swiglu_bwd(const void* gu, const void* dact, void* dgu, int M, int F, void* stream);
+/* compute_loss, slamkit/model/unit_lm.py:13-29: fp32 upcast, shift, CE(ignore_index=-100), sum/num_items (or mean
+ * over valid tokens when num_items <= 0).  logits bf16 [B*T, ldl] with V valid columns; labels int64 [B*T];
+ * dlogits (bf16, may be NULL) = d loss / d logits * dloss; partial: fp32 [2*sk_ce_blocks(M)]; row_nll fp32 [M] or
+ * NULL; stats: fp32[3] = {loss, n_valid_targets, nll_sum}. */
+int sk_ce_blocks(int M);
+int sk_ce_fwd_bwd(const void* logits, const int64_t* labels, void* dlogits, float* partial, float* row_nll,
+                  float* stats, int M, int T, int V, int ldl, float num_items, float dloss, void* stream);
+
+/* ---- attention -------------------------------------------------------------------------------------------------
+ * softmax(q k^T * scale [causal]) v with grouped-query heads, head_dim 64; q/k/v are column slices (pitch ld) of the
+ * fused projection output, o is [B*T, ldo]; lse fp32 [B,H,T].  Replaces SDPA/FA2 behind HF Qwen2Attention
+ * (HF:models/qwen2/modeling_qwen2.py:187-246) and HubertAttention (HF:models/hubert/modeling_hubert.py:262-345). */
+int sk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int T, int H, int KVH, int ld,
+                int ldo, int causal, float scale, void* stream);
+int sk_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                float* delta, void* dq, void* dk, void* dv, int B, int T, int H, int KVH, int ld, int ldo, int ldg,
+                int causal, float scale, void* stream);
+
+/* ---- optimiser ----------------------------------------------------------------------------------------------------
+ * Gradient clipping + AdamW as HF Trainer runs them (HF:trainer.py clip_grad_norm_ then torch.optim.AdamW(fused)):
+ * config/training_args/default.yaml:4-9 (lr 1e-3, max_grad_norm 0.5), betas (0.9,0.999), eps 1e-8, wd 0.
+ * bf16 parameters AND bf16 moment buffers (params are created in bf16: config/model/slam.yaml:9). */
+/* chunk tables (device): chunk_start int64[n_chunks], chunk_len int32[n_chunks], tensor_chunk_begin int32[n_tensors+1];
+ * partial fp32[n_chunks]; stats fp32[3] = {total_norm, clip_coef, exact_fp32_norm}. emulate_bf16=1 rounds per-tensor
+ * norms, the total and the coefficient to bf16 like torch does on bf16 gradients. */
+int sk_grad_norm(const void* grads, const int64_t* chunk_start, const int32_t* chunk_len, int n_chunks,
+                 const int32_t* tensor_chunk_begin, int n_tensors, float* partial, float max_norm, int emulate_bf16,
+                 float* stats, void* stream);
+/* One fused pass over the flat parameter buffer (14 B/param). clip_stats: the stats buffer of sk_grad_norm or NULL. */
+int sk_adamw_step(void* params, const void* grads, void* exp_avg, void* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, const float* clip_stats, void* stream);
+
+/* ---- causal-LM train step (path (ii)) ---------------------------------------------------------------------------
+ * One object per model replica; replaces UnitLM.forward + compute_loss + autograd backward
+ * (slamkit/model/unit_lm.py:13-29,135-182 -> HF Qwen2ForCausalLM, HF:models/qwen2/modeling_qwen2.py:417-487) and,
+ * with sk_grad_norm/sk_adamw_step, the HF Trainer inner step (HF:trainer.py:1867-2014). */
+typedef struct SkLmConfig {
+  int32_t vocab_size;        /* 502 for unit_hubert_25 (slamkit/tokeniser/unit_tokeniser.py:33-47) */
+  int32_t hidden;            /* 896 */
+  int32_t n_layers;          /* 24 */
+  int32_t n_heads;           /* 14 */
+  int32_t n_kv_heads;        /* 2 */
+  int32_t head_dim;          /* 64 (only 64 is supported) */
+  int32_t ffn;               /* 4864 */
+  int32_t max_positions;     /* rows of the RoPE tables */
+  float rms_eps;             /* 1e-6 */
+  int32_t tie_embeddings;    /* 1: lm_head shares the embedding table */
+  int32_t qkv_bias;          /* 1 for Qwen2 */
+} SkLmConfig;
+typedef struct SkLm SkLm;
+
+int sk_lm_create(const SkLmConfig* cfg, SkLm** out);
+void sk_lm_destroy(SkLm* lm);
+/* Flat parameter layout (bf16 elements). Tensors are enumerated in a fixed order; name_buf receives e.g.
+ * "layers.3.wqkv". Returns the number of tensors when idx < 0. */
+int64_t sk_lm_param_count(const SkLm* lm);
+int sk_lm_tensor_info(const SkLm* lm, int idx, char* name_buf, int name_cap, int64_t* offset, int32_t* rows,
+                      int32_t* cols);
+int64_t sk_lm_workspace_bytes(const SkLm* lm, int B, int T);
+/* Bind caller-owned memory: params/grads are flat bf16 [param_count]; rope tables bf16 [max_positions, head_dim/2];
+ * workspace >= sk_lm_workspace_bytes(B,T) for the largest (B,T) used. */
+int sk_lm_bind(SkLm* lm, void* params, void* grads, const void* rope_cos, const void* rope_sin, void* workspace,
+               int64_t workspace_bytes);
+/* Forward only (eval / log-likelihood): logits stay in the workspace, see sk_lm_logits. labels may be NULL. */
+int sk_lm_forward(SkLm* lm, const int64_t* ids, const int64_t* labels, const int32_t* pos_ids, int B, int T,
+                  float num_items, float* stats, void* stream);
+/* Forward + backward of one micro-batch. accumulate=0 overwrites grads, 1 adds (gradient accumulation).
+ * stats fp32[3] = {loss, n_valid_targets, nll_sum}. loss = nll_sum/num_items when num_items > 0
+ * (HF:trainer.py:2092-2154 num_items_in_batch semantics), else mean over valid targets. */
+int sk_lm_forward_backward(SkLm* lm, const int64_t* ids, const int64_t* labels, const int32_t* pos_ids, int B, int T,
+                           float num_items, float dloss, int accumulate, float* stats, void* stream);
+/* bf16 [B*T, sk_lm_logits_ld()] logits of the last forward (valid columns: vocab_size). */
+const void* sk_lm_logits(const SkLm* lm);
+int sk_lm_logits_ld(const SkLm* lm);
+/* Clip (max_norm <= 0 disables) + AdamW over the bound params/grads; moments are caller-owned flat bf16 buffers.
+ * stats fp32[3] as sk_grad_norm. */
+int sk_lm_optimizer_step(SkLm* lm, void* exp_avg, void* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, int step, float max_grad_norm, int emulate_bf16_norm, float* stats,
+                         void* stream);
+/* number of kernels this library launched since load (bench.py's gpu_launches) */
+int64_t sk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMKIT_B200_H */

@@ -1,0 +1,113 @@
+// extern "C" surface of libslamkit_b200.so for the op-level entry points (see include/slamkit_b200.h), plus the
+// error / device-info plumbing.  The handle-level entry points live in lm_step.cu and hubert_step.cu.
+#include "kernels.h"
+#include "../../include/slamkit_b200.h"
+#include <atomic>
+#include <stdarg.h>
+#include <stdio.h>
+
+namespace {
+thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+}  // namespace
+
+void sk_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void sk_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sk_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+#define S(x) ((cudaStream_t)(x))
+#define BF(x) (reinterpret_cast<bf16*>(x))
+#define CBF(x) (reinterpret_cast<const bf16*>(x))
+
+extern "C" {
+
+const char* sk_last_error(void) { return g_err; }
+int sk_version(void) { return 1; }
+int sk_device_sm_count(void) { return sk_num_sms(); }
+int sk_device_cc(void) {
+  int dev = 0, ma = 0, mi = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+  cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev);
+  return 10 * ma + mi;
+}
+int64_t sk_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int sk_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                 int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
+                 int force_bn, void* stream) {
+  SK_REQUIRE(A && B && C, "sk_gemm_bf16: null operand");
+  return sk_gemm_launch(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, out_f32, bias, residual, ldr, round_before_res, act,
+                        force_bn, S(stream));
+}
+int sk_embed_fwd(const int64_t* ids, const void* table, void* out, int M, int D, int V, void* stream) {
+  return sk_embed_fwd_launch(ids, CBF(table), BF(out), M, D, V, S(stream));
+}
+int sk_embed_bwd(const int64_t* ids, const void* dx, float* scratch, void* dtable, int M, int D, int V, int Vpad,
+                 int accumulate, void* stream) {
+  return sk_embed_bwd_launch(ids, CBF(dx), scratch, BF(dtable), M, D, V, Vpad, accumulate, S(stream));
+}
+int sk_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int D, float eps, void* stream) {
+  return sk_rmsnorm_fwd_launch(CBF(x), CBF(w), BF(y), rstd, M, D, eps, S(stream));
+}
+int sk_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                   void* dw, float* dw_partial, int M, int D, int accumulate_dw, void* stream) {
+  return sk_rmsnorm_bwd_launch(CBF(dy), CBF(x), CBF(w), rstd, CBF(dres), BF(dx), BF(dw), dw_partial, M, D,
+                               accumulate_dw, S(stream));
+}
+int sk_colsum(const void* x, void* out, float* partial, int M, int N, int ld, int accumulate, void* stream) {
+  return sk_colsum_launch(CBF(x), BF(out), partial, M, N, ld, accumulate, S(stream));
+}
+int sk_rope(void* qkv, const void* cos_t, const void* sin_t, const int32_t* pos_ids, int M, int T, int ld,
+            int n_rot_heads, int head_dim, int inverse, void* stream) {
+  return sk_rope_launch(BF(qkv), CBF(cos_t), CBF(sin_t), pos_ids, M, T, ld, n_rot_heads, head_dim, inverse, S(stream));
+}
+int sk_swiglu_fwd(const void* gu, void* act, int M, int F, void* stream) {
+  return sk_swiglu_fwd_launch(CBF(gu), BF(act), M, F, S(stream));
+}
+int sk_swiglu_bwd(const void* gu, const void* dact, void* dgu, int M, int F, void* stream) {
+  return sk_swiglu_bwd_launch(CBF(gu), CBF(dact), BF(dgu), M, F, S(stream));
+}
+int sk_ce_fwd_bwd(const void* logits, const int64_t* labels, void* dlogits, float* partial, float* row_nll,
+                  float* stats, int M, int T, int V, int ldl, float num_items, float dloss, void* stream) {
+  return sk_ce_launch(CBF(logits), labels, BF(dlogits), partial, row_nll, stats, M, T, V, ldl, num_items, dloss,
+                      S(stream));
+}
+int sk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int T, int H, int KVH, int ld,
+                int ldo, int causal, float scale, void* stream) {
+  return sk_attn_fwd_launch(CBF(q), CBF(k), CBF(v), BF(o), lse, B, T, H, KVH, ld, ldo, causal, scale, S(stream));
+}
+int sk_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                float* delta, void* dq, void* dk, void* dv, int B, int T, int H, int KVH, int ld, int ldo, int ldg,
+                int causal, float scale, void* stream) {
+  return sk_attn_bwd_launch(CBF(q), CBF(k), CBF(v), CBF(o), CBF(d_o), lse, delta, BF(dq), BF(dk), BF(dv), B, T, H, KVH,
+                            ld, ldo, ldg, causal, scale, S(stream));
+}
+int sk_grad_norm(const void* grads, const int64_t* chunk_start, const int32_t* chunk_len, int n_chunks,
+                 const int32_t* tensor_chunk_begin, int n_tensors, float* partial, float max_norm, int emulate_bf16,
+                 float* stats, void* stream) {
+  return sk_gradnorm_launch(CBF(grads), reinterpret_cast<const long*>(chunk_start), chunk_len, n_chunks,
+                            tensor_chunk_begin, n_tensors, partial, max_norm, emulate_bf16, stats, S(stream));
+}
+int sk_adamw_step(void* params, const void* grads, void* exp_avg, void* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, const float* clip_stats, void* stream) {
+  return sk_adamw_launch(BF(params), CBF(grads), BF(exp_avg), BF(exp_avg_sq), (long)n, lr, beta1, beta2, eps,
+                         weight_decay, step, clip_stats, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// Internal C++ launcher declarations shared by api.cu / lm_step.cu / hubert_step.cu.
+// (The public, C-ABI surface is include/slamkit_b200.h.)
+#pragma once
+#include "common.cuh"
+
+// gemm_tcgen05.cu
+int sk_make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_outer);
+int sk_pick_bn(int M, int N, int force_bn);
+int sk_gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                   int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
+                   int force_bn, cudaStream_t stream);
+
+// lm_kernels.cu
+int sk_embed_fwd_launch(const int64_t* ids, const bf16* E, bf16* out, int M, int D, int V, cudaStream_t s);
+int sk_embed_bwd_launch(const int64_t* ids, const bf16* dx, float* scratch, bf16* dE, int M, int D, int V, int Vpad,
+                        int accumulate, cudaStream_t s);
+int sk_rmsnorm_fwd_launch(const bf16* x, const bf16* w, bf16* y, float* rstd, int M, int D, float eps, cudaStream_t s);
+extern "C" int sk_rmsnorm_bwd_blocks(void);
+int sk_rmsnorm_bwd_launch(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx,
+                          bf16* dw, float* dw_partial, int M, int D, int accumulate_dw, cudaStream_t s);
+extern "C" int sk_colsum_splits(void);
+int sk_colsum_launch(const bf16* x, bf16* out, float* partial, int M, int N, int ld, int accumulate, cudaStream_t s);
+int sk_rope_launch(bf16* qkv, const bf16* cos_t, const bf16* sin_t, const int* pos_ids, int M, int T, int ld,
+                   int n_rot_heads, int head_dim, int inverse, cudaStream_t s);
+int sk_swiglu_fwd_launch(const bf16* gu, bf16* act, int M, int F, cudaStream_t s);
+int sk_swiglu_bwd_launch(const bf16* gu, const bf16* dact, bf16* dgu, int M, int F, cudaStream_t s);
+extern "C" int sk_ce_blocks(int M);
+int sk_ce_launch(const bf16* logits, const int64_t* labels, bf16* dlogits, float* partial, float* row_nll,
+                 float* stats_out, int M, int T, int V, int ldl, float num_items, float dloss, cudaStream_t s);
+int sk_gradnorm_launch(const bf16* g, const long* chunk_start, const int* chunk_len, int n_chunks,
+                       const int* tensor_chunk_begin, int n_tensors, float* partial, float max_norm, int emulate_bf16,
+                       float* stats_out, cudaStream_t s);
+int sk_adamw_launch(bf16* p, const bf16* g, bf16* m, bf16* v, long n, float lr, float beta1, float beta2, float eps,
+                    float wd, int step, const float* clip_stats, cudaStream_t s);
+int sk_transpose_launch(const bf16* in, bf16* out, int M, int N, cudaStream_t s);
+
+// attention.cu
+int sk_attn_fwd_launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int T, int H, int KVH,
+                       int ld, int ldo, int causal, float scale, cudaStream_t s);
+int sk_attn_bwd_launch(const bf16* q, const bf16* k, const bf16* v, const bf16* o, const bf16* d_o, const float* lse,
+                       float* delta, bf16* dq, bf16* dk, bf16* dv, int B, int T, int H, int KVH, int ld, int ldo,
+                       int ldg, int causal, float scale, cudaStream_t s);

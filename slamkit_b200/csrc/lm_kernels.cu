@@ -1,0 +1,713 @@
+// HBM-bound kernels of the causal-LM train step (path (ii)): embedding gather/scatter,
+// RMSNorm fwd/bwd, RoPE fwd/bwd, SwiGLU fwd/bwd, bias-grad column sums, cross-entropy fwd+bwd, gradient-norm
+// clipping and fused AdamW.  All use 128-bit coalesced global accesses and warp-shuffle reductions; bf16 storage,
+// fp32 math.  Rounding points follow the HF bf16 path so that parity with the reference is tight
+// (HF:models/qwen2/modeling_qwen2.py:35-48 MLP, :102-146 RoPE, :249-262 RMSNorm).
+#include "kernels.h"
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int MAX_VEC_PER_LANE = 4;  // supports D <= 4*32*8 = 1024
+
+// ------------------------------------------------------------------------------------------------
+// embedding
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ E, bf16* __restrict__ out,
+                                 int M, int D, int V) {
+  const int vec_per_row = D / 8;
+  const long total = (long)M * vec_per_row;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / vec_per_row);
+    const int c = (int)(i % vec_per_row);
+    long id = ids[m];
+    if (id < 0 || id >= V) id = 0;
+    stg128(out + (size_t)m * D + c * 8, ldg128(E + (size_t)id * D + c * 8));
+  }
+}
+
+// dE_f32[ids[m], :] += dx[m, :]   (fp32 atomics into a zeroed scratch; vocab is tiny so collisions are heavy but
+// the traffic is negligible next to the GEMMs)
+__global__ void embed_bwd_scatter_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ dx,
+                                         float* __restrict__ scratch, int M, int D, int V) {
+  const int vec_per_row = D / 8;
+  const long total = (long)M * vec_per_row;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / vec_per_row);
+    const int c = (int)(i % vec_per_row);
+    long id = ids[m];
+    if (id < 0 || id >= V) continue;
+    const uint4 v = ldg128_stream(dx + (size_t)m * D + c * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float* dst = scratch + (size_t)id * D + c * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(w[k]);
+      atomicAdd(dst + 2 * k, f.x);
+      atomicAdd(dst + 2 * k + 1, f.y);
+    }
+  }
+}
+
+// grad[i] = bf16(float(grad[i]) * keep + scratch[i])
+__global__ void add_f32_into_bf16_kernel(bf16* __restrict__ grad, const float* __restrict__ scratch, long n, int keep) {
+  for (long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 8; i < n; i += (long)gridDim.x * blockDim.x * 8) {
+    const float4 a = *reinterpret_cast<const float4*>(scratch + i);
+    const float4 b = *reinterpret_cast<const float4*>(scratch + i + 4);
+    float s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (keep) {
+      const uint4 g = *reinterpret_cast<const uint4*>(grad + i);
+      const uint32_t w[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16(w[k]);
+        s[2 * k] += f.x;
+        s[2 * k + 1] += f.y;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(s[0], s[1]);
+    o.y = pack_bf16(s[2], s[3]);
+    o.z = pack_bf16(s[4], s[5]);
+    o.w = pack_bf16(s[6], s[7]);
+    stg128(grad + i, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm:  y = w * bf16(x * rsqrt(mean(x^2) + eps))      one warp per row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                   float* __restrict__ rstd_out, int M, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (row >= M) return;
+  const int nvec = D / 8;
+  uint4 xv[MAX_VEC_PER_LANE];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nvec) {
+      xv[j] = ldg128_stream(x + (size_t)row * D + c * 8);
+      const uint32_t u[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16(u[k]);
+        ss += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / (float)D + eps);
+  if (lane == 0 && rstd_out) rstd_out[row] = rstd;
+#pragma unroll
+  for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nvec) {
+      const uint4 wv = ldg128(w + c * 8);
+      const uint32_t u[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
+      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16(u[k]);
+        const float2 g = unpack_bf16(ww[k]);
+        o[k] = pack_bf16(g.x * bf16_round(f.x * rstd), g.y * bf16_round(f.y * rstd));
+      }
+      stg128(y + (size_t)row * D + c * 8, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
+// backward: g = dy*w ; xhat = x*rstd ; dx = rstd*(g - xhat*mean(g*xhat)) (+ dres) ; dw partial = sum_rows dy*bf16(xhat)
+// grid-stride over rows so every block owns a fixed slice; per-block partial dw rows are written to `dw_partial`
+// [gridDim.x, D] and reduced by rmsnorm_dw_reduce_kernel in a fixed order (deterministic).
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                   const float* __restrict__ rstd_in, const bf16* __restrict__ dres, bf16* __restrict__ dx,
+                   float* __restrict__ dw_partial, int M, int D) {
+  extern __shared__ float sdw[];  // [WARPS_PER_BLOCK][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = D / 8;
+  float dwacc[MAX_VEC_PER_LANE][8];
+#pragma unroll
+  for (int j = 0; j < MAX_VEC_PER_LANE; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dwacc[j][k] = 0.f;
+  uint4 wv[MAX_VEC_PER_LANE];
+#pragma unroll
+  for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nvec) wv[j] = ldg128(w + c * 8);
+  }
+  for (int row = blockIdx.x * WARPS_PER_BLOCK + warp; row < M; row += gridDim.x * WARPS_PER_BLOCK) {
+    const float rstd = rstd_in[row];
+    float g[MAX_VEC_PER_LANE][8], xh[MAX_VEC_PER_LANE][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
+      const int c = lane + 32 * j;
+      if (c < nvec) {
+        const uint4 xv = ldg128_stream(x + (size_t)row * D + c * 8);
+        const uint4 dv = ldg128_stream(dy + (size_t)row * D + c * 8);
+        const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+        const uint32_t du[4] = {dv.x, dv.y, dv.z, dv.w};
+        const uint32_t wu[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 xf = unpack_bf16(xu[k]);
+          const float2 df = unpack_bf16(du[k]);
+          const float2 wf = unpack_bf16(wu[k]);
+          const float xh0 = xf.x * rstd, xh1 = xf.y * rstd;
+          xh[j][2 * k] = xh0;
+          xh[j][2 * k + 1] = xh1;
+          g[j][2 * k] = bf16_round(df.x * wf.x);
+          g[j][2 * k + 1] = bf16_round(df.y * wf.y);
+          dot += g[j][2 * k] * xh0 + g[j][2 * k + 1] * xh1;
+          dwacc[j][2 * k] += df.x * bf16_round(xh0);
+          dwacc[j][2 * k + 1] += df.y * bf16_round(xh1);
+        }
+      }
+    }
+    dot = warp_sum(dot) / (float)D;
+#pragma unroll
+    for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
+      const int c = lane + 32 * j;
+      if (c < nvec) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = rstd * (g[j][k] - xh[j][k] * dot);
+        if (dres) {
+          const uint4 rv = ldg128_stream(dres + (size_t)row * D + c * 8);
+          const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 rf = unpack_bf16(ru[k]);
+            o[2 * k] += rf.x;
+            o[2 * k + 1] += rf.y;
+          }
+        }
+        stg128(dx + (size_t)row * D + c * 8,
+               make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7])));
+      }
+    }
+  }
+  // block reduce dw
+#pragma unroll
+  for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sdw[warp * D + c * 8 + k] = dwacc[j][k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < WARPS_PER_BLOCK; ++wi) s += sdw[wi * D + i];
+    dw_partial[(size_t)blockIdx.x * D + i] = s;
+  }
+}
+
+// out[j] = bf16( (accumulate ? out[j] : 0) + sum_b partial[b][j] )
+__global__ void colsum_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int nblocks, int D,
+                                     int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * D + j];
+  if (accumulate) s += __bfloat162float(out[j]);
+  out[j] = __float2bfloat16_rn(s);
+}
+
+// column sums of a bf16 [M, N] matrix (leading dim ld) -> partial[gridDim.y][N]; used for the q/k/v bias gradient
+__global__ void colsum_partial_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int M, int N, int ld) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (col >= N) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per;
+  const int r1 = min(M, r0 + rows_per);
+  for (int r = r0; r < r1; ++r) {
+    const uint4 v = ldg128_stream(x + (size_t)r * ld + col);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(u[k]);
+      acc[2 * k] += f.x;
+      acc[2 * k + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) partial[(size_t)blockIdx.y * N + col + k] = acc[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE (rotate_half form), in place on the q and k head slices of the fused qkv activation [M, ld].
+//   out[i]      = bf16(bf16(x[i]*c) + bf16(-x[i+hd/2]*s))
+//   out[i+hd/2] = bf16(bf16(x[i+hd/2]*c) + bf16(x[i]*s))          c,s: bf16 tables [maxpos, hd/2]
+// inverse=1 applies the transposed rotation (backward).
+// ------------------------------------------------------------------------------------------------
+__global__ void rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
+                            const int* __restrict__ pos_ids, int M, int T, int ld, int n_rot_heads, int head_dim,
+                            int inverse) {
+  const int half = head_dim / 2;          // 32
+  const int vec_per_head = half / 8;      // 4 threads per (token, head)
+  const long total = (long)M * n_rot_heads * vec_per_head;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec_per_head);
+    const int h = (int)((i / vec_per_head) % n_rot_heads);
+    const int m = (int)(i / ((long)vec_per_head * n_rot_heads));
+    const int pos = pos_ids ? pos_ids[m] : (m % T);
+    bf16* p1 = qkv + (size_t)m * ld + h * head_dim + v * 8;
+    bf16* p2 = p1 + half;
+    const uint4 a = *reinterpret_cast<const uint4*>(p1);
+    const uint4 b = *reinterpret_cast<const uint4*>(p2);
+    const uint4 cv = ldg128(cos_t + (size_t)pos * half + v * 8);
+    const uint4 sv = ldg128(sin_t + (size_t)pos * half + v * 8);
+    const uint32_t au[4] = {a.x, a.y, a.z, a.w}, bu[4] = {b.x, b.y, b.z, b.w};
+    const uint32_t cu[4] = {cv.x, cv.y, cv.z, cv.w}, su[4] = {sv.x, sv.y, sv.z, sv.w};
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x1 = unpack_bf16(au[k]), x2 = unpack_bf16(bu[k]);
+      const float2 c = unpack_bf16(cu[k]);
+      float2 s = unpack_bf16(su[k]);
+      if (inverse) { s.x = -s.x; s.y = -s.y; }
+      o1[k] = pack_bf16(bf16_round(x1.x * c.x) + bf16_round(-x2.x * s.x), bf16_round(x1.y * c.y) + bf16_round(-x2.y * s.y));
+      o2[k] = pack_bf16(bf16_round(x2.x * c.x) + bf16_round(x1.x * s.x), bf16_round(x2.y * c.y) + bf16_round(x1.y * s.y));
+    }
+    *reinterpret_cast<uint4*>(p1) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    *reinterpret_cast<uint4*>(p2) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SwiGLU: gu = [gate | up] (each F wide).  act = bf16(bf16(silu(g)) * u)
+// ------------------------------------------------------------------------------------------------
+SK_DEVINL float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int M, int F) {
+  const int vec_per_row = F / 8;
+  const long total = (long)M * vec_per_row;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / vec_per_row);
+    const int c = (int)(i % vec_per_row);
+    const uint4 gv = ldg128_stream(gu + (size_t)m * 2 * F + c * 8);
+    const uint4 uv = ldg128_stream(gu + (size_t)m * 2 * F + F + c * 8);
+    const uint32_t g[4] = {gv.x, gv.y, gv.z, gv.w}, u[4] = {uv.x, uv.y, uv.z, uv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 gf = unpack_bf16(g[k]), uf = unpack_bf16(u[k]);
+      o[k] = pack_bf16(bf16_round(silu_f(gf.x)) * uf.x, bf16_round(silu_f(gf.y)) * uf.y);
+    }
+    stg128(act + (size_t)m * F + c * 8, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// d_gu = [ d_act*u*silu'(g) | d_act*silu(g) ]
+__global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dact, bf16* __restrict__ dgu,
+                                  int M, int F) {
+  const int vec_per_row = F / 8;
+  const long total = (long)M * vec_per_row;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / vec_per_row);
+    const int c = (int)(i % vec_per_row);
+    const uint4 gv = ldg128_stream(gu + (size_t)m * 2 * F + c * 8);
+    const uint4 uv = ldg128_stream(gu + (size_t)m * 2 * F + F + c * 8);
+    const uint4 dv = ldg128_stream(dact + (size_t)m * F + c * 8);
+    const uint32_t g[4] = {gv.x, gv.y, gv.z, gv.w}, u[4] = {uv.x, uv.y, uv.z, uv.w}, d[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t og[4], ou[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 gf = unpack_bf16(g[k]), uf = unpack_bf16(u[k]), df = unpack_bf16(d[k]);
+      const float s0 = 1.0f / (1.0f + __expf(-gf.x)), s1 = 1.0f / (1.0f + __expf(-gf.y));
+      const float sil0 = bf16_round(gf.x * s0), sil1 = bf16_round(gf.y * s1);
+      const float ds0 = s0 * (1.0f + gf.x * (1.0f - s0)), ds1 = s1 * (1.0f + gf.y * (1.0f - s1));
+      // d(silu)*u rounded like the bf16 autograd chain: d_silu = bf16(dact*u); dg = bf16(d_silu * silu'(g))
+      og[k] = pack_bf16(bf16_round(df.x * uf.x) * ds0, bf16_round(df.y * uf.y) * ds1);
+      ou[k] = pack_bf16(df.x * sil0, df.y * sil1);
+    }
+    stg128(dgu + (size_t)m * 2 * F + c * 8, make_uint4(og[0], og[1], og[2], og[3]));
+    stg128(dgu + (size_t)m * 2 * F + F + c * 8, make_uint4(ou[0], ou[1], ou[2], ou[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross entropy over bf16 logits [M, ldl] with V valid columns; shifted labels (row (b,t) predicts labels[b,t+1]).
+// Matches slamkit/model/unit_lm.py:13-29: fp32 upcast, ignore_index=-100, reduction sum (then / num_items) or mean.
+// One warp per row.  Writes per-block partial {loss_sum, n_valid} and dlogits (bf16, unscaled = softmax - onehot);
+// the scale 1/num_items (or 1/n_valid) * dloss is applied by ce_scale_kernel once the count is known when reduction
+// is 'mean'; for the 'sum / num_items' path the scale is known up front and applied here.
+// ------------------------------------------------------------------------------------------------
+constexpr int CE_MAX_VEC = 2;  // up to 512 padded columns per row
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+ce_fwd_bwd_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ labels, bf16* __restrict__ dlogits,
+                  float* __restrict__ partial /*[grid][2]*/, float* __restrict__ row_nll /*[M] or null*/, int M, int T,
+                  int V, int ldl, float grad_scale) {
+  __shared__ float s_loss[WARPS_PER_BLOCK], s_cnt[WARPS_PER_BLOCK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WARPS_PER_BLOCK + warp;
+  float my_loss = 0.f, my_cnt = 0.f;
+  if (row < M) {
+    const int t = row % T;
+    long target = -100;
+    if (t < T - 1) target = labels[row + 1];
+    const bool valid = (target >= 0 && target < V);
+    float v[CE_MAX_VEC][8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < CE_MAX_VEC; ++j) {
+      const int c = (lane + 32 * j) * 8;
+      if (c < ldl) {
+        const uint4 lv = ldg128_stream(logits + (size_t)row * ldl + c);
+        const uint32_t u[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16(u[k]);
+          v[j][2 * k] = (c + 2 * k < V) ? f.x : -INFINITY;
+          v[j][2 * k + 1] = (c + 2 * k + 1 < V) ? f.y : -INFINITY;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mx = fmaxf(mx, v[j][k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[j][k] = -INFINITY;
+      }
+    }
+    mx = warp_max(mx);
+    float se = 0.f, tgt_logit = 0.f;
+#pragma unroll
+    for (int j = 0; j < CE_MAX_VEC; ++j) {
+      const int c = (lane + 32 * j) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        se += expf(v[j][k] - mx);
+        if (valid && c + k == (int)target) tgt_logit = v[j][k];
+      }
+    }
+    se = warp_sum(se);
+    tgt_logit = warp_sum(tgt_logit);
+    const float lse = mx + logf(se);
+    if (valid) {
+      my_loss = lse - tgt_logit;
+      my_cnt = 1.f;
+    }
+    if (row_nll && lane == 0) row_nll[row] = valid ? (lse - tgt_logit) : 0.f;
+    if (dlogits) {
+      const float inv = 1.0f / se;
+#pragma unroll
+      for (int j = 0; j < CE_MAX_VEC; ++j) {
+        const int c = (lane + 32 * j) * 8;
+        if (c < ldl) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float pr = valid ? expf(v[j][k] - mx) * inv : 0.f;
+            if (valid && c + k == (int)target) pr -= 1.f;
+            o[k] = pr * grad_scale;
+          }
+          stg128(dlogits + (size_t)row * ldl + c,
+                 make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7])));
+        }
+      }
+    }
+  }
+  if (lane == 0) { s_loss[warp] = my_loss; s_cnt[warp] = my_cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < WARPS_PER_BLOCK; ++i) { a += s_loss[i]; b += s_cnt[i]; }
+    partial[2 * blockIdx.x] = a;
+    partial[2 * blockIdx.x + 1] = b;
+  }
+}
+
+// out[0] = loss (sum/denom), out[1] = n_valid, out[2] = raw nll sum.   denom<=0 -> mean over valid tokens.
+__global__ void ce_finalize_kernel(const float* __restrict__ partial, int nblocks, float denom, float* __restrict__ out) {
+  __shared__ double sa[256], sb[256];
+  double a = 0, b = 0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+  sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double d = denom > 0.f ? (double)denom : (sb[0] > 0 ? sb[0] : 1.0);
+    out[0] = (float)(sa[0] / d);
+    out[1] = (float)sb[0];
+    out[2] = (float)sa[0];
+  }
+}
+
+// dlogits *= 1/n_valid (mean reduction, count only known after the forward pass)
+__global__ void scale_by_inv_count_kernel(bf16* __restrict__ x, long n, const float* __restrict__ stats) {
+  const float sc = 1.0f / fmaxf(stats[1], 1.0f);
+  for (long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 8; i < n; i += (long)gridDim.x * blockDim.x * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(x + i);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(u[k]);
+      o[k] = pack_bf16(f.x * sc, f.y * sc);
+    }
+    stg128(x + i, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gradient norm (torch.nn.utils.clip_grad_norm_ semantics on bf16 grads) + fused AdamW
+// ------------------------------------------------------------------------------------------------
+// chunk c covers grads[chunk_start[c] .. +chunk_len[c]) and never straddles a tensor; partial[c] = sum of squares
+__global__ void sumsq_chunks_kernel(const bf16* __restrict__ g, const long* __restrict__ chunk_start,
+                                    const int* __restrict__ chunk_len, float* __restrict__ partial) {
+  __shared__ float sred[32];
+  const long s = chunk_start[blockIdx.x];
+  const int n = chunk_len[blockIdx.x];
+  float acc = 0.f;
+  const int nvec = n / 8;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 v = ldg128_stream(g + s + (long)i * 8);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(u[k]);
+      acc += f.x * f.x + f.y * f.y;
+    }
+  }
+  for (int i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x) {
+    const float f = __bfloat162float(g[s + i]);
+    acc += f * f;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+
+// one block: per-tensor norms (rounded to bf16 like torch._foreach_norm on bf16 grads), total norm (bf16), and
+// clip coefficient  min(1, max_norm/(total+1e-6))  (bf16, as torch computes it on bf16 tensors).
+// out[0] = total_norm, out[1] = clip_coef (1.0 if max_norm <= 0), out[2] = exact fp32 total norm
+__global__ void gradnorm_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ tensor_chunk_begin,
+                                         int n_tensors, float max_norm, int emulate_bf16, float* __restrict__ out) {
+  __shared__ double s1[256], s2[256];
+  double a = 0, b = 0;
+  for (int t = threadIdx.x; t < n_tensors; t += blockDim.x) {
+    float ss = 0.f;
+    for (int c = tensor_chunk_begin[t]; c < tensor_chunk_begin[t + 1]; ++c) ss += partial[c];
+    float nt = sqrtf(ss);
+    b += (double)ss;
+    if (emulate_bf16) nt = bf16_round(nt);
+    a += (double)nt * (double)nt;
+  }
+  s1[threadIdx.x] = a; s2[threadIdx.x] = b;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { s1[threadIdx.x] += s1[threadIdx.x + s]; s2[threadIdx.x] += s2[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float total = sqrtf((float)s1[0]);
+    if (emulate_bf16) total = bf16_round(total);
+    float coef = 1.0f;
+    if (max_norm > 0.f) {
+      coef = max_norm / (total + 1e-6f);
+      if (emulate_bf16) coef = bf16_round(coef);
+      coef = fminf(coef, 1.0f);
+    }
+    out[0] = total;
+    out[1] = coef;
+    out[2] = sqrtf((float)s2[0]);
+  }
+}
+
+// torch fused AdamW semantics (fp32 math per element, bf16 storage of p, m, v; decoupled weight decay):
+//   g = bf16(g * clip_coef) ; p -= lr*wd*p ; m = m + (1-b1)*(g-m) ; v = b2*v + (1-b2)*g*g
+//   p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void adamw_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, bf16* __restrict__ m,
+                             bf16* __restrict__ v, long n, float lr, float beta1, float beta2, float eps, float wd,
+                             float bc1, float bc2_sqrt, const float* __restrict__ clip_stats) {
+  const float coef = clip_stats ? clip_stats[1] : 1.0f;
+  const float step_size = lr / bc1;
+  for (long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 8; i < n; i += (long)gridDim.x * blockDim.x * 8) {
+    const uint4 pv = *reinterpret_cast<const uint4*>(p + i);
+    const uint4 gv = ldg128_stream(g + i);
+    const uint4 mv = *reinterpret_cast<const uint4*>(m + i);
+    const uint4 vv = *reinterpret_cast<const uint4*>(v + i);
+    const uint32_t pu[4] = {pv.x, pv.y, pv.z, pv.w}, gu[4] = {gv.x, gv.y, gv.z, gv.w};
+    const uint32_t mu[4] = {mv.x, mv.y, mv.z, mv.w}, vu[4] = {vv.x, vv.y, vv.z, vv.w};
+    uint32_t po[4], mo[4], vo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 pf = unpack_bf16(pu[k]), gf = unpack_bf16(gu[k]), mf = unpack_bf16(mu[k]), vf = unpack_bf16(vu[k]);
+      float pp[2] = {pf.x, pf.y}, gg[2] = {gf.x, gf.y}, mm[2] = {mf.x, mf.y}, vv2[2] = {vf.x, vf.y};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float grad = (coef != 1.0f) ? bf16_round(gg[e] * coef) : gg[e];
+        float param = pp[e];
+        param -= lr * wd * param;
+        float ea = mm[e] + (1.0f - beta1) * (grad - mm[e]);
+        float es = beta2 * vv2[e] + (1.0f - beta2) * grad * grad;
+        const float denom = sqrtf(es) / bc2_sqrt + eps;
+        param -= step_size * ea / denom;
+        pp[e] = param; mm[e] = ea; vv2[e] = es;
+      }
+      po[k] = pack_bf16(pp[0], pp[1]);
+      mo[k] = pack_bf16(mm[0], mm[1]);
+      vo[k] = pack_bf16(vv2[0], vv2[1]);
+    }
+    stg128(p + i, make_uint4(po[0], po[1], po[2], po[3]));
+    stg128(m + i, make_uint4(mo[0], mo[1], mo[2], mo[3]));
+    stg128(v + i, make_uint4(vo[0], vo[1], vo[2], vo[3]));
+  }
+}
+
+// out[N, M] = in[M, N]^T (bf16), 32x32 tiles through shared memory; used only by tests / the transposed-copy fallback
+__global__ void transpose_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int M, int N) {
+  __shared__ bf16 tile[32][33];
+  int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
+  for (int j = 0; j < 32; j += 8)
+    if (x < N && y + j < M) tile[threadIdx.y + j][threadIdx.x] = in[(size_t)(y + j) * N + x];
+  __syncthreads();
+  x = blockIdx.y * 32 + threadIdx.x;
+  y = blockIdx.x * 32 + threadIdx.y;
+  for (int j = 0; j < 32; j += 8)
+    if (x < M && y + j < N) out[(size_t)(y + j) * M + x] = tile[threadIdx.x][threadIdx.y + j];
+}
+
+inline int grid_for(long work_items, int threads, int max_blocks_per_sm = 16) {
+  long b = (work_items + threads - 1) / threads;
+  long cap = (long)sk_num_sms() * max_blocks_per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers (C++ linkage; the extern "C" ABI in api.cu forwards to these)
+// ------------------------------------------------------------------------------------------------
+int sk_embed_fwd_launch(const int64_t* ids, const bf16* E, bf16* out, int M, int D, int V, cudaStream_t s) {
+  SK_REQUIRE(D % 8 == 0, "embed: D must be a multiple of 8");
+  embed_fwd_kernel<<<grid_for((long)M * D / 8, 256), 256, 0, s>>>(ids, E, out, M, D, V);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_embed_bwd_launch(const int64_t* ids, const bf16* dx, float* scratch, bf16* dE, int M, int D, int V, int Vpad,
+                        int accumulate, cudaStream_t s) {
+  SK_REQUIRE(D % 8 == 0, "embed: D must be a multiple of 8");
+  SK_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)Vpad * D * sizeof(float), s));
+  embed_bwd_scatter_kernel<<<grid_for((long)M * D / 8, 256), 256, 0, s>>>(ids, dx, scratch, M, D, V);
+  SK_LAUNCH_CHECK();
+  add_f32_into_bf16_kernel<<<grid_for((long)Vpad * D / 8, 256), 256, 0, s>>>(dE, scratch, (long)Vpad * D, accumulate);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_rmsnorm_fwd_launch(const bf16* x, const bf16* w, bf16* y, float* rstd, int M, int D, float eps, cudaStream_t s) {
+  SK_REQUIRE(D % 8 == 0 && D <= 1024, "rmsnorm: D must be a multiple of 8 and <= 1024 (D=%d)", D);
+  rmsnorm_fwd_kernel<<<(M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, y, rstd, M, D, eps);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+// dw_partial must hold sk_rmsnorm_bwd_blocks() * D floats
+extern "C" int sk_rmsnorm_bwd_blocks(void) { return sk_num_sms() * 2; }
+int sk_rmsnorm_bwd_launch(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx,
+                          bf16* dw, float* dw_partial, int M, int D, int accumulate_dw, cudaStream_t s) {
+  SK_REQUIRE(D % 8 == 0 && D <= 1024, "rmsnorm: D must be a multiple of 8 and <= 1024 (D=%d)", D);
+  int blocks = sk_rmsnorm_bwd_blocks();
+  const int need = (M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  if (blocks > need) blocks = need;
+  const size_t smem = (size_t)WARPS_PER_BLOCK * D * sizeof(float);
+  rmsnorm_bwd_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, s>>>(dy, x, w, rstd, dres, dx, dw_partial, M, D);
+  SK_LAUNCH_CHECK();
+  colsum_reduce_kernel<<<(D + 255) / 256, 256, 0, s>>>(dw_partial, dw, blocks, D, accumulate_dw);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+constexpr int COLSUM_SPLITS = 64;
+extern "C" int sk_colsum_splits(void) { return COLSUM_SPLITS; }
+int sk_colsum_launch(const bf16* x, bf16* out, float* partial, int M, int N, int ld, int accumulate, cudaStream_t s) {
+  SK_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
+  dim3 grid((N / 8 + 127) / 128, COLSUM_SPLITS);
+  colsum_partial_kernel<<<grid, 128, 0, s>>>(x, partial, M, N, ld);
+  SK_LAUNCH_CHECK();
+  colsum_reduce_kernel<<<(N + 255) / 256, 256, 0, s>>>(partial, out, COLSUM_SPLITS, N, accumulate);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_rope_launch(bf16* qkv, const bf16* cos_t, const bf16* sin_t, const int* pos_ids, int M, int T, int ld,
+                   int n_rot_heads, int head_dim, int inverse, cudaStream_t s) {
+  SK_REQUIRE(head_dim % 16 == 0 && ld % 8 == 0, "rope: head_dim must be a multiple of 16");
+  rope_kernel<<<grid_for((long)M * n_rot_heads * (head_dim / 16), 256), 256, 0, s>>>(qkv, cos_t, sin_t, pos_ids, M, T, ld,
+                                                                                   n_rot_heads, head_dim, inverse);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_swiglu_fwd_launch(const bf16* gu, bf16* act, int M, int F, cudaStream_t s) {
+  SK_REQUIRE(F % 8 == 0, "swiglu: F must be a multiple of 8");
+  swiglu_fwd_kernel<<<grid_for((long)M * F / 8, 256), 256, 0, s>>>(gu, act, M, F);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_swiglu_bwd_launch(const bf16* gu, const bf16* dact, bf16* dgu, int M, int F, cudaStream_t s) {
+  SK_REQUIRE(F % 8 == 0, "swiglu: F must be a multiple of 8");
+  swiglu_bwd_kernel<<<grid_for((long)M * F / 8, 256), 256, 0, s>>>(gu, dact, dgu, M, F);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sk_ce_blocks(int M) { return (M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; }
+// stats_out: float[3] = {loss, n_valid, nll_sum}.  num_items > 0: loss = sum/num_items (reference 'sum' path);
+// num_items <= 0: mean over valid tokens.  dloss scales the gradient.
+int sk_ce_launch(const bf16* logits, const int64_t* labels, bf16* dlogits, float* partial, float* row_nll,
+                 float* stats_out, int M, int T, int V, int ldl, float num_items, float dloss, cudaStream_t s) {
+  SK_REQUIRE(ldl % 8 == 0 && ldl <= CE_MAX_VEC * 256, "ce: padded vocab must be a multiple of 8 and <= %d", CE_MAX_VEC * 256);
+  const int blocks = sk_ce_blocks(M);
+  const float gs = num_items > 0.f ? dloss / num_items : dloss;
+  ce_fwd_bwd_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(logits, labels, dlogits, partial, row_nll, M, T, V, ldl, gs);
+  SK_LAUNCH_CHECK();
+  ce_finalize_kernel<<<1, 256, 0, s>>>(partial, blocks, num_items, stats_out);
+  SK_LAUNCH_CHECK();
+  if (dlogits && num_items <= 0.f) {
+    scale_by_inv_count_kernel<<<grid_for((long)M * ldl / 8, 256), 256, 0, s>>>(dlogits, (long)M * ldl, stats_out);
+    SK_LAUNCH_CHECK();
+  }
+  return 0;
+}
+int sk_gradnorm_launch(const bf16* g, const long* chunk_start, const int* chunk_len, int n_chunks,
+                       const int* tensor_chunk_begin, int n_tensors, float* partial, float max_norm, int emulate_bf16,
+                       float* stats_out, cudaStream_t s) {
+  sumsq_chunks_kernel<<<n_chunks, 256, 0, s>>>(g, chunk_start, chunk_len, partial);
+  SK_LAUNCH_CHECK();
+  gradnorm_finalize_kernel<<<1, 256, 0, s>>>(partial, tensor_chunk_begin, n_tensors, max_norm, emulate_bf16, stats_out);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_adamw_launch(bf16* p, const bf16* g, bf16* m, bf16* v, long n, float lr, float beta1, float beta2, float eps,
+                    float wd, int step, const float* clip_stats, cudaStream_t s) {
+  SK_REQUIRE(n % 8 == 0, "adamw: flat parameter count must be a multiple of 8 (n=%ld)", n);
+  SK_REQUIRE(step >= 1, "adamw: step counts from 1");
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  adamw_kernel<<<grid_for(n / 8, 256, 8), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, clip_stats);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_transpose_launch(const bf16* in, bf16* out, int M, int N, cudaStream_t s) {
+  dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(in, out, M, N);
+  SK_LAUNCH_CHECK();
+  return 0;
+}

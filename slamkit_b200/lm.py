@@ -1,0 +1,297 @@
+"""B200UnitLM -- host-side mirror of the reference's TokenLM plugin for hot path (ii).
+
+Mirrors `slamkit.model.unit_lm.UnitLM` (slamkit/model/unit_lm.py:82-212) and the `TokenLM` ABC
+(slamkit/model/token_lm.py:7-27): same `forward(input_ids, attention_mask, position_ids, labels,
+num_items_in_batch)` contract, `log_likelihood`, HF-compatible state-dict names (`lm.model.layers.N...`), but the
+compute is the hand-written sm_100a train step behind the C ABI (`sk_lm_*` in include/slamkit_b200.h).  PyTorch only
+owns the flat bf16 parameter / gradient / workspace buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, Iterator, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+@dataclass
+class LMConfig:
+    """Shape of the decoder (defaults = Qwen2.5-0.5B body with the 502-entry unit vocab, config/model/slam.yaml)."""
+    vocab_size: int = 502
+    hidden: int = 896
+    n_layers: int = 24
+    n_heads: int = 14
+    n_kv_heads: int = 2
+    head_dim: int = 64
+    ffn: int = 4864
+    max_positions: int = 2048
+    rms_eps: float = 1e-6
+    rope_theta: float = 10000.0          # config/model/slam.yaml:8 (see SURVEY.md §3.2 RoPE-theta hazard)
+    tie_embeddings: bool = True
+    qkv_bias: bool = True
+    pad_token_id: int = 0
+
+    @staticmethod
+    def from_hf(cfg, vocab_size: Optional[int] = None, max_positions: int = 2048) -> "LMConfig":
+        rp = getattr(cfg, "rope_parameters", None) or {}
+        theta = rp.get("rope_theta", getattr(cfg, "rope_theta", 10000.0))
+        return LMConfig(
+            vocab_size=vocab_size or cfg.vocab_size, hidden=cfg.hidden_size, n_layers=cfg.num_hidden_layers,
+            n_heads=cfg.num_attention_heads, n_kv_heads=cfg.num_key_value_heads,
+            head_dim=getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads,
+            ffn=cfg.intermediate_size, max_positions=max_positions, rms_eps=cfg.rms_norm_eps, rope_theta=float(theta),
+            tie_embeddings=bool(cfg.tie_word_embeddings), qkv_bias=True, pad_token_id=cfg.pad_token_id or 0)
+
+
+def rope_tables(theta: float, head_dim: int, max_positions: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """cos/sin tables exactly as HF computes them (HF:models/qwen2/modeling_qwen2.py Qwen2RotaryEmbedding.forward):
+    fp32 inv_freq, fp32 outer product, cos()/sin(), then cast to the activation dtype (bf16). Shape [P, head_dim/2]."""
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).to(dtype=torch.float) / head_dim))
+    pos = torch.arange(max_positions, dtype=torch.float32)
+    freqs = (inv_freq[:, None].float() @ pos[None, :].float()).transpose(0, 1)  # [P, hd/2]
+    return freqs.cos().to(torch.bfloat16).contiguous(), freqs.sin().to(torch.bfloat16).contiguous()
+
+
+@dataclass
+class LMOutput:
+    loss: Optional[torch.Tensor]
+    logits: Optional[torch.Tensor]
+    stats: Optional[torch.Tensor] = None   # device fp32[3]: loss, n_valid_targets, nll_sum
+
+
+class B200UnitLM:
+    """Causal unit LM whose forward/backward/optimiser run in libslamkit_b200.so."""
+
+    def __init__(self, config: LMConfig, device: str = "cuda:0", max_batch: int = 8, max_seq: int = 1024,
+                 trainable: bool = True, seed: Optional[int] = None):
+        self.lib = L.require_cuda()
+        self.config = config
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        c = L.SkLmConfig(config.vocab_size, config.hidden, config.n_layers, config.n_heads, config.n_kv_heads,
+                         config.head_dim, config.ffn, config.max_positions, config.rms_eps,
+                         int(config.tie_embeddings), int(config.qkv_bias))
+        self._h = C.c_void_p()
+        L.check(self.lib.sk_lm_create(C.byref(c), C.byref(self._h)))
+        self.n_params = int(self.lib.sk_lm_param_count(self._h))
+        self.tensors: Dict[str, Tuple[int, int, int]] = {}
+        n = self.lib.sk_lm_tensor_info(self._h, -1, None, 0, None, None, None)
+        buf = C.create_string_buffer(64)
+        for i in range(n):
+            off, r, cc = C.c_int64(), C.c_int32(), C.c_int32()
+            L.check(self.lib.sk_lm_tensor_info(self._h, i, buf, 64, C.byref(off), C.byref(r), C.byref(cc)))
+            self.tensors[buf.value.decode()] = (off.value, r.value, cc.value)
+        self.vocab_padded = self.tensors["embed"][1]
+        self.params = torch.zeros(self.n_params, device=self.device, dtype=torch.bfloat16)
+        self.grads = torch.zeros(self.n_params, device=self.device, dtype=torch.bfloat16) if trainable else None
+        cos, sin = rope_tables(config.rope_theta, config.head_dim, config.max_positions)
+        self.rope_cos, self.rope_sin = cos.to(self.device), sin.to(self.device)
+        self.max_batch, self.max_seq = max_batch, max_seq
+        self.workspace = None
+        self._bind(max_batch, max_seq)
+        self.stats = torch.zeros(3, device=self.device, dtype=torch.float32)
+        if seed is not None:
+            self.init_weights(seed)
+
+    # ---- memory ------------------------------------------------------------------------------------------------
+    def _bind(self, B: int, T: int) -> None:
+        need = int(self.lib.sk_lm_workspace_bytes(self._h, B, T))
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = torch.empty(need, device=self.device, dtype=torch.uint8)
+        L.check(self.lib.sk_lm_bind(self._h, L.ptr(self.params), L.ptr(self.grads), L.ptr(self.rope_cos),
+                                    L.ptr(self.rope_sin), L.ptr(self.workspace), C.c_int64(self.workspace.numel())))
+
+    def _ensure(self, B: int, T: int) -> None:
+        need = int(self.lib.sk_lm_workspace_bytes(self._h, B, T))
+        if need > self.workspace.numel():
+            self._bind(B, T)
+
+    def tensor(self, name: str, grad: bool = False) -> torch.Tensor:
+        off, r, c = self.tensors[name]
+        flat = self.grads if grad else self.params
+        return flat[off:off + r * c].view(r, c)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.sk_lm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- weights -----------------------------------------------------------------------------------------------
+    def init_weights(self, seed: int = 0, std: float = 0.02) -> None:
+        """HF `_init_weights` equivalent: normal(0, std) for linear/embedding weights, zeros for biases, ones for
+        norms (HF:modeling_utils.py PreTrainedModel._init_weights)."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        V = self.config.vocab_size
+        for name, (off, r, c) in self.tensors.items():
+            t = self.params[off:off + r * c].view(r, c)
+            base = name.split(".")[-1]
+            if base in ("ln1", "ln2", "final_norm"):
+                t.fill_(1.0)
+            elif base == "bqkv":
+                t.zero_()
+            elif base in ("embed", "lm_head"):
+                t.zero_()
+                t[:V].copy_((torch.randn((V, c), generator=g) * std).to(torch.bfloat16))
+            else:
+                t.copy_((torch.randn((r, c), generator=g) * std).to(torch.bfloat16))
+
+    def _hf_map(self) -> Iterator[Tuple[str, str, int, int]]:
+        """(flat tensor name, HF parameter name, row offset inside the flat tensor, n rows)."""
+        cfg = self.config
+        q, kv = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
+        for l in range(cfg.n_layers):
+            p, h = f"layers.{l}.", f"lm.model.layers.{l}."
+            yield p + "ln1", h + "input_layernorm.weight", 0, 1
+            yield p + "wqkv", h + "self_attn.q_proj.weight", 0, q
+            yield p + "wqkv", h + "self_attn.k_proj.weight", q, kv
+            yield p + "wqkv", h + "self_attn.v_proj.weight", q + kv, kv
+            yield p + "bqkv", h + "self_attn.q_proj.bias", 0, q
+            yield p + "bqkv", h + "self_attn.k_proj.bias", q, kv
+            yield p + "bqkv", h + "self_attn.v_proj.bias", q + kv, kv
+            yield p + "wo", h + "self_attn.o_proj.weight", 0, cfg.hidden
+            yield p + "ln2", h + "post_attention_layernorm.weight", 0, 1
+            yield p + "wgu", h + "mlp.gate_proj.weight", 0, cfg.ffn
+            yield p + "wgu", h + "mlp.up_proj.weight", cfg.ffn, cfg.ffn
+            yield p + "wd", h + "mlp.down_proj.weight", 0, cfg.hidden
+        yield "final_norm", "lm.model.norm.weight", 0, 1
+        yield "embed", "lm.model.embed_tokens.weight", 0, cfg.vocab_size
+        if not cfg.tie_embeddings:
+            yield "lm_head", "lm.lm_head.weight", 0, cfg.vocab_size
+
+    def load_hf_state_dict(self, sd: Dict[str, torch.Tensor], grads: bool = False) -> None:
+        """Load parameters named as in `UnitLM.state_dict()` (prefix `lm.`, slamkit/model/unit_lm.py:87)."""
+        for flat, hf, row0, nrows in self._hf_map():
+            src = sd[hf]
+            dst = self.tensor(flat, grad=grads)
+            if flat.endswith("bqkv") or src.dim() == 1:
+                if flat.endswith("bqkv"):
+                    dst.view(-1)[row0:row0 + nrows].copy_(src.to(torch.bfloat16))
+                else:
+                    dst.view(-1).copy_(src.to(torch.bfloat16))
+            else:
+                dst[row0:row0 + nrows].copy_(src.to(torch.bfloat16))
+
+    def state_dict_hf(self, grads: bool = False) -> Dict[str, torch.Tensor]:
+        out = {}
+        for flat, hf, row0, nrows in self._hf_map():
+            t = self.tensor(flat, grad=grads)
+            if flat.endswith("bqkv"):
+                out[hf] = t.view(-1)[row0:row0 + nrows].clone()
+            elif t.shape[0] == 1:
+                out[hf] = t.view(-1).clone()
+            else:
+                out[hf] = t[row0:row0 + nrows].clone()
+        if self.config.tie_embeddings:
+            out["lm.lm_head.weight"] = out["lm.model.embed_tokens.weight"]
+        return out
+
+    # ---- compute -----------------------------------------------------------------------------------------------
+    @staticmethod
+    def _labels_with_mask(input_ids, labels, attention_mask):
+        return labels
+
+    def _prep(self, input_ids: torch.Tensor, position_ids: Optional[torch.Tensor]):
+        assert input_ids.dim() == 2 and input_ids.dtype == torch.int64
+        B, T = input_ids.shape
+        self._ensure(B, T)
+        ids = input_ids.to(self.device, non_blocking=True).contiguous()
+        pos = None
+        if position_ids is not None:
+            pos = position_ids.to(self.device, non_blocking=True).to(torch.int32).contiguous().view(-1)
+        return B, T, ids, pos
+
+    def logits_view(self, B: int, T: int) -> torch.Tensor:
+        """Zero-copy view of the bf16 logits of the last forward: [B, T, vocab_size]."""
+        p = self.lib.sk_lm_logits(self._h)
+        ld = self.lib.sk_lm_logits_ld(self._h)
+        off = p - self.workspace.data_ptr()
+        flat = self.workspace[off:off + B * T * ld * 2].view(torch.bfloat16).view(B, T, ld)
+        return flat[:, :, :self.config.vocab_size]
+
+    def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                num_items_in_batch: Optional[float] = None, **_) -> LMOutput:
+        """Forward only (eval / scoring). Padding is right-padding as produced by the reference collators
+        (slamkit/data/hf_dataset.py:61-64), so the causal mask alone is exact for the non-pad positions."""
+        B, T, ids, pos = self._prep(input_ids, position_ids)
+        lab = labels.to(self.device).contiguous() if labels is not None else None
+        ni = float(num_items_in_batch) if num_items_in_batch is not None else 0.0
+        L.check(self.lib.sk_lm_forward(self._h, L.ptr(ids), L.ptr(lab), L.ptr(pos), B, T, L.f32(ni), L.ptr(self.stats),
+                                       L.stream_ptr()))
+        return LMOutput(loss=self.stats[0] if labels is not None else None, logits=self.logits_view(B, T),
+                        stats=self.stats)
+
+    __call__ = forward
+
+    def forward_backward(self, input_ids: torch.Tensor, labels: torch.Tensor, position_ids: Optional[torch.Tensor] = None,
+                         num_items_in_batch: Optional[float] = None, loss_scale: float = 1.0,
+                         accumulate: bool = False) -> LMOutput:
+        """One micro-batch of training: loss (slamkit/model/unit_lm.py:13-29 semantics) and gradients into self.grads."""
+        B, T, ids, pos = self._prep(input_ids, position_ids)
+        lab = labels.to(self.device, non_blocking=True).contiguous()
+        ni = float(num_items_in_batch) if num_items_in_batch is not None else 0.0
+        L.check(self.lib.sk_lm_forward_backward(self._h, L.ptr(ids), L.ptr(lab), L.ptr(pos), B, T, L.f32(ni),
+                                                L.f32(loss_scale), int(accumulate), L.ptr(self.stats), L.stream_ptr()))
+        return LMOutput(loss=self.stats[0], logits=None, stats=self.stats)
+
+    @torch.inference_mode()
+    def log_likelihood(self, tokens: torch.Tensor, mean_nll: bool, ignore_tokens=None) -> torch.Tensor:
+        """TokenLM.log_likelihood (slamkit/model/unit_lm.py:184-194): per-sample (mean or summed) log-likelihood."""
+        out = self.forward(tokens)
+        logits = out.logits.float()
+        if ignore_tokens is not None:
+            logits[:, :, ignore_tokens] = float("-inf")
+        x = tokens.to(self.device)[..., 1:].clone()
+        x[x == self.config.pad_token_id] = -100
+        lp = torch.log_softmax(logits[..., :-1, :], dim=-1)
+        mask = x.ne(-100)
+        tok = lp.gather(-1, x.clamp(min=0).unsqueeze(-1)).squeeze(-1) * mask
+        ll = tok.sum(-1)
+        return ll / mask.sum(-1) if mean_nll else ll
+
+    def generate(self, *a, **k):
+        raise NotImplementedError("generation (KV-cache decode) is outside the B200 hot path (SURVEY.md §2 row 3)")
+
+
+class B200AdamW:
+    """Gradient clipping + AdamW exactly as HF Trainer applies them (HF:trainer.py clip_grad_norm_ -> optimizer.step):
+    one `sk_lm_optimizer_step` call = grad-norm reduction + fused clip-scale/AdamW pass over the flat buffers."""
+
+    def __init__(self, model: B200UnitLM, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, max_grad_norm: float = 0.5, emulate_bf16_norm: bool = True):
+        self.model = model
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        self.emulate = emulate_bf16_norm
+        self.exp_avg = torch.zeros_like(model.params)
+        self.exp_avg_sq = torch.zeros_like(model.params)
+        self.step_count = 0
+        self.stats = torch.zeros(3, device=model.device, dtype=torch.float32)  # total_norm, clip_coef, exact norm
+
+    def step(self, lr: Optional[float] = None) -> None:
+        self.step_count += 1
+        m = self.model
+        L.check(m.lib.sk_lm_optimizer_step(m._h, L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                                           L.f32(self.lr if lr is None else lr), L.f32(self.betas[0]),
+                                           L.f32(self.betas[1]), L.f32(self.eps), L.f32(self.wd), self.step_count,
+                                           L.f32(self.max_grad_norm or 0.0), int(self.emulate), L.ptr(self.stats),
+                                           L.stream_ptr()))
+
+
+def cosine_with_min_lr(step: int, *, base_lr: float, min_lr: float, warmup_steps: int, total_steps: int,
+                       num_cycles: float = 0.5) -> float:
+    """HF `get_cosine_with_min_lr_schedule_with_warmup` (HF:optimization.py:326-385) evaluated at `step`."""
+    min_lr_rate = min_lr / base_lr
+    if step < warmup_steps:
+        return base_lr * float(step) / float(max(1, warmup_steps))
+    progress = float(step - warmup_steps) / float(max(1, total_steps - warmup_steps))
+    factor = 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress))
+    factor = factor * (1 - min_lr_rate) + min_lr_rate
+    return base_lr * max(0, factor)
