@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native slamkit hot path.
+
+Default workload (BASELINE.json configs[1]): one optimiser step of the SLAM pre-training recipe -- Qwen2.5-0.5B-shaped
+unit LM (358 M params, vocab 502, bf16 params and optimiser state), per-GPU micro-batch [8, 1024] synthetic unit
+tokens, gradient clip 0.5 + AdamW -- data-parallel over N GPUs with one NCCL gradient all-reduce per step.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (one JSON line on rank 0)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference's algorithm on the host cores
+
+`value`  : speech-tokens/s, inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : same metric through the public API with HOST inputs: per step a pinned-host -> device copy of ids/labels
+           and a device -> host read of the loss inside the timed region.
+`roofline`: the dominant kernel (tcgen05 GEMM, ~290 launches/step) timed live with CUDA events on its launching stream
+           in a separate profiling step; algorithmic FLOPs = 6 * N_matmul_params * tokens.
+`cpu_baseline`: oracle/lm_oracle.OracleTrainer (the pinned restatement of the reference's HF path) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SEQ = 1024
+PER_GPU_BATCH = 8
+N_MATMUL_PARAMS = 24 * 14_909_440 + 502 * 896
+FLOP_PER_TOKEN = 6 * N_MATMUL_PARAMS + 3 * 24 * (4 * SEQ * 896) // 2   # 2.2818 GFLOP (causal-halved attention)
+GEMM_FLOP_PER_TOKEN = 6 * N_MATMUL_PARAMS
+
+
+def synth_batch(rank: int, idx: int, B: int = PER_GPU_BATCH, T: int = SEQ) -> torch.Tensor:
+    """position 0 = BOS(1), the rest uniform in [2,501] with immediate repeats re-drawn (dedup)."""
+    g = torch.Generator().manual_seed(1234 + rank + 1000 * idx)
+    ids = torch.randint(2, 502, (B, T), generator=g)
+    ids[:, 0] = 1
+    for _ in range(4):
+        rep = ids[:, 1:] == ids[:, :-1]
+        if not rep.any():
+            break
+        fresh = torch.randint(2, 502, (B, T - 1), generator=g)
+        ids[:, 1:] = torch.where(rep, fresh, ids[:, 1:])
+    return ids
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_burst": d.get("bf16_tflops"), "bf16_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "B200_PROFILING.md (of fallback)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report that instead of failing the bench
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def run_reference(args, rank: int, world: int):
+    """The reference's own algorithm on the host cores (oracle port: HF Qwen2 + compute_loss + clip + AdamW restated in
+    plain torch, pinned to the reference by tests/golden/lm_tiny.npz).  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import lm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.OracleLMConfig()
+    tr = O.OracleTrainer(O.init_params(cfg, seed=0), cfg, lr=1e-3, max_grad_norm=0.5)
+    sample_B = 1
+    batches = [synth_batch(0, i, sample_B) for i in range(2)]
+    for i in range(args.warmup):
+        tr.train_step(batches[i % 2], batches[i % 2].clone())
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        tr.train_step(batches[i % 2], batches[i % 2].clone())
+    dt = time.perf_counter() - t0
+    tok_s = sample_B * SEQ * args.steps / dt
+    line = {"impl": "reference", "metric": "speech-tokens/sec (SLAM seq=1024)", "value": tok_s, "unit": "tokens/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world),
+            "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.steps} optimiser steps on a [{sample_B},{SEQ}] micro-batch of the same model"},
+            "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world: int):
+    return {"workload": "SLAM pretrain step: Qwen2.5-0.5B-shaped unit LM (358M, vocab 502), unit_hubert_25 tokens, "
+                        "seq=1024, per-GPU micro-batch 8, clip 0.5 + AdamW, bf16 params/state",
+            "global_batch": PER_GPU_BATCH * world, "seq_len": SEQ, "parallelism": f"dp{world}",
+            "l2": "working set ~11 GB/step per GPU (activations + params + optimiser state) >> 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from slamkit_b200 import _lib
+    from slamkit_b200.lm import B200AdamW, B200UnitLM, LMConfig
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.require_cuda()
+
+    model = B200UnitLM(LMConfig(), device=str(dev), max_batch=PER_GPU_BATCH, max_seq=SEQ, seed=0)
+    opt = B200AdamW(model, lr=1e-3, max_grad_norm=0.5)
+    n_items = float(PER_GPU_BATCH * SEQ * world)      # HF num_items_in_batch gathered over ranks (HF:trainer.py:2136)
+    NB = 4
+    host = [synth_batch(rank, i).pin_memory() for i in range(NB)]
+    devb = [h.to(dev) for h in host]
+
+    def step_device(i):
+        model.forward_backward(devb[i % NB], devb[i % NB], num_items_in_batch=n_items)
+        if world > 1:
+            dist.all_reduce(model.grads)              # SUM: every rank already divided by the global token count
+        opt.step()
+
+    def step_e2e(i):
+        ids = host[i % NB].to(dev, non_blocking=True)  # labels = ids (causal LM): one H2D copy feeds both
+        model.forward_backward(ids, ids, num_items_in_batch=n_items)
+        if world > 1:
+            dist.all_reduce(model.grads)
+        opt.step()
+        return float(model.stats[0].item())           # D2H read of the loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.sk_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_device(i)
+    e1.record()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = lib.sk_launch_count() - launches0
+
+    # end-to-end through the public API with host buffers
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e2.record()
+    loss = 0.0
+    for i in range(args.steps):
+        loss = step_e2e(i)
+    e3.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e2.elapsed_time(e3), wall_ms))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    tokens_per_step = PER_GPU_BATCH * SEQ * world
+    value = tokens_per_step * args.steps / (dev_ms / 1e3)
+    e2e_value = tokens_per_step * args.steps / (e2e_ms / 1e3)
+
+    # live per-category device timing of one step (outside the timed regions)
+    import ctypes as C
+    pk = peaks()
+    roof = None
+    if rank == 0:
+        lib.sk_prof_enable(1)
+        reps = 3
+        for i in range(reps):
+            model.forward_backward(devb[i % NB], devb[i % NB], num_items_in_batch=n_items)
+            opt.step()
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        lib.sk_prof_collect(ms, cnt)
+        lib.sk_prof_enable(0)
+        gemm_ms, attn_ms, opt_ms = ms[0] / reps, ms[1] / reps, ms[2] / reps
+        step_ms = dev_ms / args.steps
+        gemm_tf = GEMM_FLOP_PER_TOKEN * PER_GPU_BATCH * SEQ / (gemm_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel ({cnt[0] // reps} launches/step)",
+                "achieved": gemm_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": gemm_tf / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained",
+                "algorithmic_flops_per_step": GEMM_FLOP_PER_TOKEN * PER_GPU_BATCH * SEQ,
+                "share_of_step": gemm_ms / step_ms,
+                "breakdown_ms": {"gemm": gemm_ms, "attention": attn_ms, "optimizer": opt_ms,
+                                 "other": max(step_ms - gemm_ms - attn_ms - opt_ms, 0.0), "step": step_ms},
+                "step_tflops": FLOP_PER_TOKEN * PER_GPU_BATCH * SEQ / (step_ms / 1e3) / 1e12 / world * world,
+                "step_frac_of_peak": FLOP_PER_TOKEN * PER_GPU_BATCH * SEQ / (step_ms / 1e3) / 1e12 / pk["bf16_sustained"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import lm_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        ocfg = O.OracleLMConfig()
+        tr = O.OracleTrainer(O.init_params(ocfg, seed=0), ocfg, lr=1e-3, max_grad_norm=0.5)
+        b = synth_batch(0, 0, 1)
+        tr.train_step(b, b.clone())
+        t0 = time.perf_counter()
+        n = 3
+        for _ in range(n):
+            tr.train_step(b, b.clone())
+        dt = time.perf_counter() - t0
+        cpu = {"value": SEQ * n / dt, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n} optimiser steps on a [1,{SEQ}] micro-batch of the same 358M model (1 warm-up)"}
+
+    if rank == 0:
+        line = {"metric": "speech-tokens/sec (SLAM seq=1024)", "value": value, "unit": "tokens/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(world), "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": PER_GPU_BATCH * SEQ * 8,
+                        "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "final_loss": loss}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,11 @@ int sk_lm_optimizer_step(SkLm* lm, void* exp_avg, void* exp_avg_sq, float lr, fl
                          void* stream);
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 int64_t sk_launch_count(void);
+/* Bench-only device timing: when enabled, CUDA events are recorded on the launching stream around every launch of
+ * category 0 (tcgen05 GEMM), 1 (attention), 2 (optimiser).  sk_prof_collect synchronises the device and returns the
+ * summed milliseconds and launch-group counts per category (arrays of 4), then resets. */
+int sk_prof_enable(int on);
+int sk_prof_collect(double* ms_by_cat, int64_t* count_by_cat);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
+#include <vector>
 
 namespace {
 thread_local char g_err[1024] = "";
@@ -18,6 +19,28 @@ void sk_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void sk_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-category device timing (bench.py's roofline leg): CUDA events recorded around the launches of one
+// category on the launching stream.  Off by default; never active inside bench.py's timed region.
+namespace {
+constexpr int PROF_CATS = 4;
+constexpr int PROF_MAX = 8192;
+bool g_prof_on = false;
+std::vector<cudaEvent_t> g_prof_ev;
+std::vector<int> g_prof_cat;
+int g_prof_used = 0;
+}  // namespace
+void sk_prof_begin(int cat, cudaStream_t s) {
+  if (!g_prof_on || g_prof_used + 2 > PROF_MAX) return;
+  cudaEventRecord(g_prof_ev[g_prof_used], s);
+  g_prof_cat[g_prof_used / 2] = cat;
+  g_prof_used += 1;
+}
+void sk_prof_end(cudaStream_t s) {
+  if (!g_prof_on || (g_prof_used & 1) == 0) return;
+  cudaEventRecord(g_prof_ev[g_prof_used], s);
+  g_prof_used += 1;
+}
 
 int sk_num_sms() {
   static int n = 0;
@@ -47,6 +70,29 @@ int sk_device_cc(void) {
   return 10 * ma + mi;
 }
 int64_t sk_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int sk_prof_enable(int on) {
+  if (on && g_prof_ev.empty()) {
+    g_prof_ev.resize(PROF_MAX);
+    g_prof_cat.resize(PROF_MAX / 2);
+    for (int i = 0; i < PROF_MAX; ++i) SK_CUDA_CHECK(cudaEventCreate(&g_prof_ev[i]));
+  }
+  g_prof_on = on != 0;
+  g_prof_used = 0;
+  return 0;
+}
+int sk_prof_collect(double* ms_by_cat, int64_t* count_by_cat) {
+  SK_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int c = 0; c < PROF_CATS; ++c) { ms_by_cat[c] = 0.0; count_by_cat[c] = 0; }
+  for (int i = 0; i + 1 < g_prof_used; i += 2) {
+    float ms = 0.f;
+    SK_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof_ev[i], g_prof_ev[i + 1]));
+    const int c = g_prof_cat[i / 2];
+    if (c >= 0 && c < PROF_CATS) { ms_by_cat[c] += ms; count_by_cat[c] += 1; }
+  }
+  g_prof_used = 0;
+  return 0;
+}
 
 int sk_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                  int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,

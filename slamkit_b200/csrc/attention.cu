@@ -529,8 +529,10 @@ int sk_attn_fwd_launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, flo
     init = true;
   }
   dim3 grid((T + 127) / 128, H, B);
+  sk_prof_begin(1, s);
   if (causal) attn_fwd_kernel<true><<<grid, 256, FWD_SMEM, s>>>(q, k, v, o, lse, T, ld, ldo, H, H / KVH, scale);
   else attn_fwd_kernel<false><<<grid, 256, FWD_SMEM, s>>>(q, k, v, o, lse, T, ld, ldo, H, H / KVH, scale);
+  sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;
 }
@@ -549,6 +551,7 @@ int sk_attn_bwd_launch(const bf16* q, const bf16* k, const bf16* v, const bf16* 
     init = true;
   }
   const long total = (long)B * T * H * 8;
+  sk_prof_begin(1, s);
   attn_delta_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(o, d_o, delta, B, T, H, ldo);
   SK_LAUNCH_CHECK();
   const int group = H / KVH;
@@ -562,6 +565,7 @@ int sk_attn_bwd_launch(const bf16* q, const bf16* k, const bf16* v, const bf16* 
     SK_LAUNCH_CHECK();
     attn_bwd_dq_kernel<false><<<g2, 128, DQ_SMEM, s>>>(q, k, v, d_o, lse, delta, dq, T, ld, ldo, ldg, H, group, scale);
   }
+  sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;
 }

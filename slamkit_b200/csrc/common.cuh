@@ -40,6 +40,9 @@ void sk_count_launch();
   } while (0)
 
 int sk_num_sms();
+// bench-only device timing hooks (api.cu): category 0 = tcgen05 GEMM, 1 = attention, 2 = optimiser, 3 = other
+void sk_prof_begin(int cat, cudaStream_t s);
+void sk_prof_end(cudaStream_t s);
 
 // ----------------------------------------------------------------------------------------------
 // small math / packing

@@ -294,7 +294,9 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
+  sk_prof_begin(0, stream);
   gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  sk_prof_end(stream);
   SK_LAUNCH_CHECK();
   return 0;
 }
@@ -308,12 +310,9 @@ int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorM
   return launch_gemm<BN, true, true>(tmA, tmB, p, grid, s);
 }
 
-// cycles per 16-deep k-step of one 128 x BN tile: tensor floor BN/2 vs. smem operand reads at 128 B/clk
-inline int tile_cost(int bn) {
-  int tensor = bn / 2;
-  int smem = (BM * UMMA_K * 2 + bn * UMMA_K * 2) / 128;
-  return tensor > smem ? tensor : smem;
-}
+// Relative cost of one 128 x BN tile (BN=256 == 100), measured on B200 (profiles/r01_gemm_bench.txt): narrow tiles
+// pay the per-tile pipeline fill / epilogue overhead and re-read the A tile from shared memory more often per FLOP.
+inline int tile_cost(int bn) { return bn >= 256 ? 100 : (bn >= 128 ? 61 : 54); }
 
 }  // namespace
 

@@ -1,0 +1,442 @@
+// HBM-bound kernels of the HuBERT unit-extraction path (path (i)):
+//   conv0 + GroupNorm(over time) + GELU front (two passes, the 12.6 GB fp32 intermediate of the reference is never
+//   materialised), LayerNorm (+ residual add), channel regrouping for the positional conv, fp32 -> bf16 hi/lo
+//   splitting, k-means argmin (first-min tie-break like sklearn) and run-length dedup.
+//
+// Activation format.  The reference computes this path in fp32 and the unit ids must match it, so bf16 tensor-core
+// GEMMs are fed "split" operands: every activation x is stored as two bf16 tensors (hi = bf16(x), lo = bf16(x - hi));
+// a GEMM then accumulates hi*hi + hi*lo + lo*hi in fp32 (error ~2^-16 per product instead of 2^-8).  Element-wise
+// kernels here read hi+lo, compute in fp32, and write hi/lo again.
+#include "kernels.h"
+#include <algorithm>
+
+namespace {
+
+SK_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+SK_DEVINL void split_store(bf16* hi, bf16* lo, size_t idx, float v) {
+  const bf16 h = __float2bfloat16_rn(v);
+  hi[idx] = h;
+  lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+SK_DEVINL void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float h0 = bf16_round(v[2 * k]), h1 = bf16_round(v[2 * k + 1]);
+    h[k] = pack_bf16(h0, h1);
+    l[k] = pack_bf16(v[2 * k] - h0, v[2 * k + 1] - h1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+SK_DEVINL void load8_hilo(const bf16* hi, const bf16* lo, size_t idx, float (&v)[8]) {
+  const uint4 a = ldg128_stream(hi + idx);
+  const uint32_t au[4] = {a.x, a.y, a.z, a.w};
+  if (lo) {
+    const uint4 b = ldg128_stream(lo + idx);
+    const uint32_t bu[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = unpack_bf16(au[k]), y = unpack_bf16(bu[k]);
+      v[2 * k] = x.x + y.x;
+      v[2 * k + 1] = x.y + y.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = unpack_bf16(au[k]);
+      v[2 * k] = x.x;
+      v[2 * k + 1] = x.y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> (hi, lo) bf16 split (weights at bind time)
+// ------------------------------------------------------------------------------------------------
+__global__ void split_f32_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    split_store(hi, lo, i, x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv0 (1 -> C channels, kernel KW, stride ST, no bias) + GroupNorm(C groups) over time + GELU.
+// Pass 1: because the input has ONE channel, the per-(clip, channel) mean and second moment of the conv output are
+// bilinear forms in the KW window sums  S[j] = sum_t x[ST t + j]  and  R[j][j'] = sum_t x[ST t + j] x[ST t + j']:
+//   sum_t y_c = sum_j w_cj S_j ,  sum_t y_c^2 = sum_jj' w_cj w_cj' R_jj'.
+// So the statistics pass reads the waveform once and never touches the C x T output.  Accumulated in fp64.
+// The (pad,pad) zero padding of the reference (F.pad(wav,(40,40))) is applied by index arithmetic.
+// ------------------------------------------------------------------------------------------------
+constexpr int KW_MAX = 10;
+constexpr int NSTAT = KW_MAX + KW_MAX * (KW_MAX + 1) / 2;  // 65
+
+SK_DEVINL float wav_at(const float* __restrict__ w, long i, int S, int pad) {
+  const long j = i - pad;
+  return (j >= 0 && j < S) ? w[j] : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+conv0_stats_kernel(const float* __restrict__ wav, double* __restrict__ stats /*[B][NSTAT]*/, int S, int pad, int T0,
+                   int KW, int ST) {
+  __shared__ double sred[8][NSTAT];
+  const int b = blockIdx.y;
+  const float* w = wav + (size_t)b * S;
+  double acc[NSTAT];
+#pragma unroll
+  for (int i = 0; i < NSTAT; ++i) acc[i] = 0.0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T0; t += gridDim.x * blockDim.x) {
+    float x[KW_MAX];
+#pragma unroll
+    for (int j = 0; j < KW_MAX; ++j) x[j] = j < KW ? wav_at(w, (long)ST * t + j, S, pad) : 0.f;
+    int q = KW_MAX;
+#pragma unroll
+    for (int j = 0; j < KW_MAX; ++j) {
+      acc[j] += (double)x[j];
+#pragma unroll
+      for (int j2 = j; j2 < KW_MAX; ++j2) acc[q++] += (double)x[j] * (double)x[j2];
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < NSTAT; ++i) {
+    double v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sred[warp][i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NSTAT; i += blockDim.x) {
+    double v = 0.0;
+    for (int wi = 0; wi < 8; ++wi) v += sred[wi][i];
+    atomicAdd(stats + (size_t)b * NSTAT + i, v);
+  }
+}
+
+// per (clip, channel): scale = gamma * rstd, shift = beta - mean * gamma * rstd
+__global__ void conv0_affine_kernel(const double* __restrict__ stats, const float* __restrict__ w /*[C][KW]*/,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    float2* __restrict__ affine /*[B][C]*/, int C, int KW, int T0, float eps) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* st = stats + (size_t)b * NSTAT;
+  double m = 0.0, e2 = 0.0;
+  int q = KW_MAX;
+  for (int j = 0; j < KW_MAX; ++j) {
+    const double wj = j < KW ? (double)w[c * KW + j] : 0.0;
+    m += wj * st[j];
+    for (int j2 = j; j2 < KW_MAX; ++j2) {
+      const double wj2 = j2 < KW ? (double)w[c * KW + j2] : 0.0;
+      e2 += (j2 == j ? 1.0 : 2.0) * wj * wj2 * st[q++];
+    }
+  }
+  m /= (double)T0;
+  e2 /= (double)T0;
+  const double var = e2 - m * m;
+  const double rstd = 1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps);
+  const double sc = (double)gamma[c] * rstd;
+  affine[(size_t)b * C + c] = make_float2((float)sc, (float)((double)beta[c] - m * sc));
+}
+
+// Pass 2: out[b, t, c] = GELU(conv(x)[c,t] * scale + shift), channels-last, hi/lo bf16.  One thread = one frame x 8
+// channels; a warp covers 256 consecutive channels of one frame -> 512 B coalesced stores per tensor.
+__global__ void __launch_bounds__(256)
+conv0_apply_kernel(const float* __restrict__ wav, const float* __restrict__ w, const float2* __restrict__ affine,
+                   bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int S, int pad, int T0, int C, int KW, int ST) {
+  extern __shared__ float s_w[];  // [C][KW] weights then [C] float2 affine
+  float2* s_aff = reinterpret_cast<float2*>(s_w + C * KW);
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < C * KW; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_aff[i] = affine[(size_t)b * C + i];
+  __syncthreads();
+  const float* wv = wav + (size_t)b * S;
+  const int groups = C / 8;                       // channel groups of 8
+  const int frames_per_block = blockDim.x / groups > 0 ? blockDim.x / groups : 1;
+  const int cg = threadIdx.x % groups;
+  const int tf = threadIdx.x / groups;
+  for (int t0 = blockIdx.x * frames_per_block; t0 < T0; t0 += gridDim.x * frames_per_block) {
+    const int t = t0 + tf;
+    if (tf >= frames_per_block || t >= T0) continue;
+    float x[KW_MAX];
+#pragma unroll
+    for (int j = 0; j < KW_MAX; ++j) x[j] = j < KW ? wav_at(wv, (long)ST * t + j, S, pad) : 0.f;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cg * 8 + k;
+      float y = 0.f;
+#pragma unroll
+      for (int j = 0; j < KW_MAX; ++j)
+        if (j < KW) y = fmaf(s_w[c * KW + j], x[j], y);
+      const float2 a = s_aff[c];
+      v[k] = gelu_erf(fmaf(y, a.x, a.y));
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const size_t idx = ((size_t)b * T0 + t) * C + cg * 8;
+    stg128(out_hi + idx, hi);
+    stg128(out_lo + idx, lo);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (biased variance, eps inside sqrt; torch.nn.LayerNorm), input = (a_hi+a_lo) [+ (b_hi+b_lo)],
+// fp32 gamma/beta, output hi/lo (+ optional fp32 copy for k-means).  One warp per row, D <= 1024.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm_hilo_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, const bf16* __restrict__ b_hi,
+                      const bf16* __restrict__ b_lo, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, float* __restrict__ o_f32, int M, int D,
+                      float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= M) return;
+  const int nvec = D / 8;
+  float v[4][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nvec) {
+      const size_t idx = (size_t)row * D + c * 8;
+      load8_hilo(a_hi, a_lo, idx, v[j]);
+      if (b_hi) {
+        float u[8];
+        load8_hilo(b_hi, b_lo, idx, u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[j][k] += u[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += v[j][k];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = v[j][k] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane + 32 * j;
+    if (c < nvec) {
+      float o[8];
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c * 8), g1 = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + c * 8), b1 = *reinterpret_cast<const float4*>(beta + c * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (v[j][k] - mean) * rstd * gg[k] + bb[k];
+      const size_t idx = (size_t)row * D + c * 8;
+      uint4 hi, lo;
+      split8(o, hi, lo);
+      stg128(o_hi + idx, hi);
+      stg128(o_lo + idx, lo);
+      if (o_f32) {
+        *reinterpret_cast<float4*>(o_f32 + idx) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(o_f32 + idx + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Positional-conv input staging: [B*T, G*cg] -> [B, T + 2*halo, G*cgp] with zero halo rows and zero pad channels
+// (cg = 48 channels per group padded to cgp = 64 so that every k-block of the grouped conv is one 128-byte TMA row).
+// ------------------------------------------------------------------------------------------------
+__global__ void regroup_pad_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
+                                   bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int T, int halo, int G,
+                                   int cg, int cgp) {
+  const int Tp = T + 2 * halo;
+  const int vec_per_row = G * cgp / 8;
+  const long total = (long)B * Tp * vec_per_row;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec_per_row);
+    const long r = i / vec_per_row;
+    const int tp = (int)(r % Tp);
+    const int b = (int)(r / Tp);
+    const int g = (v * 8) / cgp, ci = (v * 8) % cgp;
+    const int t = tp - halo;
+    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+    if (t >= 0 && t < T && ci < cg) {
+      const size_t src = ((size_t)b * T + t) * (G * cg) + g * cg + ci;
+      hi = ldg128_stream(in_hi + src);
+      lo = ldg128_stream(in_lo + src);
+    }
+    const size_t dst = ((size_t)b * Tp + tp) * (G * cgp) + v * 8;
+    stg128(out_hi + dst, hi);
+    stg128(out_lo + dst, lo);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k-means labels: label[m] = argmin_j (csq[j] - 2 * dot[m][j]), first minimum wins (SK:_k_means_lloyd.pyx:198-213).
+// dot: fp32 [M, ld] from the split GEMM; one warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+kmeans_argmin_kernel(const float* __restrict__ dot, const float* __restrict__ csq, int32_t* __restrict__ labels, int M,
+                     int U, int ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= M) return;
+  float best = INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = lane; j < U; j += 32) {
+    const float d = csq[j] + (-2.0f) * dot[(size_t)row * ld + j];
+    if (d < best) { best = d; bi = j; }   // ascending j per lane: strict '<' keeps the first minimum
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) labels[row] = bi;
+}
+
+__global__ void row_sqnorm_kernel(const float* __restrict__ c, float* __restrict__ out, int U, int D) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= U) return;
+  float s = 0.f;
+  for (int i = lane; i < D; i += 32) s += c[(size_t)warp * D + i] * c[(size_t)warp * D + i];
+  s = warp_sum(s);
+  if (lane == 0) out[warp] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Run-length dedup of each row's first n_frames[b] labels (itertools.groupby in UnitTokeniser.audio_represent,
+// slamkit/tokeniser/unit_tokeniser.py:57): units / durations / count per row.  One warp per row, ballot scan.
+// ------------------------------------------------------------------------------------------------
+__global__ void rle_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ n_frames,
+                           int32_t* __restrict__ units, int32_t* __restrict__ durations, int32_t* __restrict__ counts,
+                           int B, int T) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const int32_t* row = labels + (size_t)warp * T;
+  const int n = min(n_frames ? n_frames[warp] : T, T);
+  int n_runs = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const bool in = i < n;
+    const int cur = in ? row[i] : -1;
+    const bool head = in && (i == 0 || row[i - 1] != cur);
+    const unsigned m = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      const int slot = n_runs + __popc(m & ((1u << lane) - 1));
+      units[(size_t)warp * T + slot] = cur;
+      durations[(size_t)warp * T + slot] = i;   // start index for now
+    }
+    n_runs += __popc(m);
+  }
+  __syncwarp();
+  // convert start indices to run lengths back-to-front within each 32-chunk to avoid read-after-write hazards
+  for (int base = 0; base < n_runs; base += 32) {
+    const int s = base + lane;
+    int start = 0, next = n;
+    if (s < n_runs) {
+      start = durations[(size_t)warp * T + s];
+      next = (s + 1 < n_runs) ? durations[(size_t)warp * T + s + 1] : n;
+    }
+    __syncwarp();
+    if (s < n_runs) durations[(size_t)warp * T + s] = next - start;
+    __syncwarp();
+  }
+  if (lane == 0) counts[warp] = n_runs;
+}
+
+// rel_l = ceil(float32(lens)/S * T) as int (hubert_feature_extractor.py:46), lens int64 or NULL (-> T)
+__global__ void rel_len_kernel(const int64_t* __restrict__ lens, int32_t* __restrict__ n_frames, int B, int S, int T) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (!lens) { n_frames[b] = T; return; }
+  const float r = ((float)lens[b] / (float)S) * (float)T;
+  int v = (int)ceilf(r);
+  n_frames[b] = v < 0 ? 0 : (v > T ? T : v);
+}
+
+inline int grid_for(long work_items, int threads, int max_blocks_per_sm = 16) {
+  long b = (work_items + threads - 1) / threads;
+  const long cap = (long)sk_num_sms() * max_blocks_per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+int sk_split_f32_launch(const float* x, bf16* hi, bf16* lo, long n, cudaStream_t s) {
+  split_f32_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, hi, lo, n);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sk_conv0_nstat(void) { return NSTAT; }
+int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const float* beta, double* stats,
+                    float2* affine, bf16* out_hi, bf16* out_lo, int B, int S, int pad, int T0, int C, int KW, int ST,
+                    float eps, cudaStream_t s) {
+  SK_REQUIRE(KW <= KW_MAX, "conv0: kernel width %d > %d", KW, KW_MAX);
+  SK_REQUIRE(C % 8 == 0 && C / 8 <= 256, "conv0: channel count must be a multiple of 8 and <= 2048");
+  SK_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)B * NSTAT * sizeof(double), s));
+  dim3 g1(std::min(64, (T0 + 255) / 256), B);
+  conv0_stats_kernel<<<g1, 256, 0, s>>>(wav, stats, S, pad, T0, KW, ST);
+  SK_LAUNCH_CHECK();
+  dim3 g2((C + 127) / 128, B);
+  conv0_affine_kernel<<<g2, 128, 0, s>>>(stats, w, gamma, beta, affine, C, KW, T0, eps);
+  SK_LAUNCH_CHECK();
+  const int fpb = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
+  int gx = (T0 + fpb - 1) / fpb;
+  const int cap = std::max(1, sk_num_sms() * 8 / B);
+  if (gx > cap) gx = cap;
+  const size_t smem = (size_t)C * KW * sizeof(float) + (size_t)C * sizeof(float2);
+  static bool attr = false;
+  if (!attr) {
+    SK_CUDA_CHECK(cudaFuncSetAttribute(conv0_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  conv0_apply_kernel<<<dim3(gx, B), 256, smem, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_layernorm_hilo_launch(const bf16* a_hi, const bf16* a_lo, const bf16* b_hi, const bf16* b_lo, const float* gamma,
+                             const float* beta, bf16* o_hi, bf16* o_lo, float* o_f32, int M, int D, float eps,
+                             cudaStream_t s) {
+  SK_REQUIRE(D % 8 == 0 && D <= 1024, "layernorm: D must be a multiple of 8 and <= 1024");
+  layernorm_hilo_kernel<<<(M + 7) / 8, 256, 0, s>>>(a_hi, a_lo, b_hi, b_lo, gamma, beta, o_hi, o_lo, o_f32, M, D, eps);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_regroup_pad_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int B, int T, int halo,
+                          int G, int cg, int cgp, cudaStream_t s) {
+  SK_REQUIRE(cg % 8 == 0 && cgp % 8 == 0 && cgp >= cg, "regroup: bad group sizes");
+  regroup_pad_kernel<<<grid_for((long)B * (T + 2 * halo) * G * cgp / 8, 256), 256, 0, s>>>(in_hi, in_lo, out_hi, out_lo, B,
+                                                                                         T, halo, G, cg, cgp);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_row_sqnorm_launch(const float* c, float* out, int U, int D, cudaStream_t s) {
+  row_sqnorm_kernel<<<(U * 32 + 255) / 256, 256, 0, s>>>(c, out, U, D);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_kmeans_argmin_launch(const float* dot, const float* csq, int32_t* labels, int M, int U, int ld, cudaStream_t s) {
+  kmeans_argmin_kernel<<<(M + 7) / 8, 256, 0, s>>>(dot, csq, labels, M, U, ld);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_rle_launch(const int32_t* labels, const int32_t* n_frames, int32_t* units, int32_t* durations, int32_t* counts,
+                  int B, int T, cudaStream_t s) {
+  rle_kernel<<<(B * 32 + 127) / 128, 128, 0, s>>>(labels, n_frames, units, durations, counts, B, T);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_rel_len_launch(const int64_t* lens, int32_t* n_frames, int B, int S, int T, cudaStream_t s) {
+  rel_len_kernel<<<(B + 127) / 128, 128, 0, s>>>(lens, n_frames, B, S, T);
+  SK_LAUNCH_CHECK();
+  return 0;
+}

@@ -41,3 +41,20 @@ int sk_attn_fwd_launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, flo
 int sk_attn_bwd_launch(const bf16* q, const bf16* k, const bf16* v, const bf16* o, const bf16* d_o, const float* lse,
                        float* delta, bf16* dq, bf16* dk, bf16* dv, int B, int T, int H, int KVH, int ld, int ldo,
                        int ldg, int causal, float scale, cudaStream_t s);
+
+// hubert_kernels.cu
+int sk_split_f32_launch(const float* x, bf16* hi, bf16* lo, long n, cudaStream_t s);
+extern "C" int sk_conv0_nstat(void);
+int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const float* beta, double* stats,
+                    float2* affine, bf16* out_hi, bf16* out_lo, int B, int S, int pad, int T0, int C, int KW, int ST,
+                    float eps, cudaStream_t s);
+int sk_layernorm_hilo_launch(const bf16* a_hi, const bf16* a_lo, const bf16* b_hi, const bf16* b_lo, const float* gamma,
+                             const float* beta, bf16* o_hi, bf16* o_lo, float* o_f32, int M, int D, float eps,
+                             cudaStream_t s);
+int sk_regroup_pad_launch(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int B, int T, int halo,
+                          int G, int cg, int cgp, cudaStream_t s);
+int sk_row_sqnorm_launch(const float* c, float* out, int U, int D, cudaStream_t s);
+int sk_kmeans_argmin_launch(const float* dot, const float* csq, int32_t* labels, int M, int U, int ld, cudaStream_t s);
+int sk_rle_launch(const int32_t* labels, const int32_t* n_frames, int32_t* units, int32_t* durations, int32_t* counts,
+                  int B, int T, cudaStream_t s);
+int sk_rel_len_launch(const int64_t* lens, int32_t* n_frames, int B, int S, int T, cudaStream_t s);

@@ -395,10 +395,14 @@ int sk_lm_optimizer_step(SkLm* lm, void* exp_avg, void* exp_avg_sq, float lr, fl
   SK_REQUIRE(lm && exp_avg && exp_avg_sq && stats, "sk_lm_optimizer_step: null argument");
   SK_REQUIRE(lm->params && lm->grads, "sk_lm_optimizer_step: params/grads not bound");
   cudaStream_t s = (cudaStream_t)stream;
+  sk_prof_begin(2, s);
   SK_TRY(sk_gradnorm_launch(lm->grads, lm->d_chunk_start, lm->d_chunk_len, lm->n_chunks, lm->d_tensor_chunk_begin,
                             (int)lm->tensors.size(), lm->d_chunk_partial, max_grad_norm, emulate_bf16_norm, stats, s));
-  return sk_adamw_launch(lm->params, lm->grads, reinterpret_cast<bf16*>(exp_avg), reinterpret_cast<bf16*>(exp_avg_sq),
-                         lm->n_params, lr, beta1, beta2, eps, weight_decay, step, stats, s);
+  const int rc = sk_adamw_launch(lm->params, lm->grads, reinterpret_cast<bf16*>(exp_avg),
+                                 reinterpret_cast<bf16*>(exp_avg_sq), lm->n_params, lr, beta1, beta2, eps, weight_decay,
+                                 step, stats, s);
+  sk_prof_end(s);
+  return rc;
 }
 
 }  // extern "C"

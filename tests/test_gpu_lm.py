@@ -57,8 +57,11 @@ def test_lm_matches_reference_golden(golden_dir):
     sd_p = m.state_dict_hf()
     for k in p:
         ref = u16_to_bf16(z["new::" + k]).view_as(p[k])
+        # the first AdamW step moves every weight by ~lr*sign(grad) = 1e-3, i.e. only ~8 bf16 ulps of a 0.02-sized
+        # weight: compare the update direction and size, tolerant of sign flips on near-zero gradients
         upd, ref_upd = sd_p[k].cpu().float() - p[k].float(), ref.float() - p[k].float()
-        assert rel_err(upd, ref_upd) < 0.05, k
+        assert rel_err(upd, ref_upd) < 0.2, k
+        assert (sd_p[k].cpu() == ref).float().mean() > 0.9, k
 
 
 @pytest.mark.parametrize("B,T,layers", [(2, 200, 3), (1, 1024, 2), (3, 130, 1)])
@@ -127,8 +130,9 @@ def test_lm_full_size_properties():
     labels = ids.clone()
     out = m.forward_backward(ids, labels, num_items_in_batch=8192.0)
     loss0 = float(out.loss)
-    # random-init model: loss ~ ln(502) * 8184/8192 (8 of the 8192 positions have no target)
-    assert abs(loss0 - np.log(502) * 8184 / 8192) < 0.15, loss0
+    # random-init model with tied embeddings (std 0.02, |h| = sqrt(896)): logits ~ N(0, 0.6^2), so the loss sits
+    # ~sigma^2/2 above ln(502) (scaled by 8184/8192: 8 of the 8192 positions have no target)
+    assert 6.2 < loss0 < 6.6, loss0
     assert int(out.stats[1]) == 8 * 1023
     g0 = m.grads.clone()
     assert torch.isfinite(g0.float()).all()
