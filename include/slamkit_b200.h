@@ -142,6 +142,59 @@ int sk_lm_logits_ld(const SkLm* lm);
 int sk_lm_optimizer_step(SkLm* lm, void* exp_avg, void* exp_avg_sq, float lr, float beta1, float beta2, float eps,
                          float weight_decay, int step, float max_grad_norm, int emulate_bf16_norm, float* stats,
                          void* stream);
+/* ---- HuBERT unit extraction (path (i)) ------------------------------------------------------------------------------
+ * One object per device; replaces HubertFeatureExtractor.extract + batch_cluster
+ * (slamkit/feature_extractor/hubert_feature_extractor.py:40-50,73-81): F.pad(40,40) -> HF HubertModel conv encoder,
+ * projection, positional conv, `n_layers` encoder layers (= the reference's `layer`, hidden_states[layer]) -> k-means
+ * labels -> rel_l trim.  Weights are one flat fp32 buffer in the "prepared" layout enumerated by sk_hubert_tensor_info:
+ * conv{i}.w as [C_out, k*C_in] with (tap, in-channel) order, pos.w grouped/padded [G*64, K*64] with torch weight_norm
+ * already folded, fused wqkv/bqkv, km.centers zero-padded to a multiple of 64 rows. */
+typedef struct SkHubertConfig {
+  int32_t n_conv;                /* 8 */
+  int32_t conv_dim;              /* 512 */
+  int32_t conv_kernel[8];        /* 10,3,3,3,3,2,2,2 */
+  int32_t conv_stride[8];        /* 5,2,2,2,2,2,2,2 */
+  int32_t hidden;                /* 768 */
+  int32_t n_heads;               /* 12 (head_dim must be 64) */
+  int32_t ffn;                   /* 3072 */
+  int32_t n_layers;              /* encoder layers to RUN = config `layer` (11 for mhubert_25) */
+  int32_t pos_conv_kernel;       /* 128 */
+  int32_t pos_conv_groups;       /* 16 */
+  int32_t n_units;               /* 500 */
+  float ln_eps;                  /* 1e-5 */
+  int32_t pad;                   /* 40 */
+} SkHubertConfig;
+typedef struct SkHubert SkHubert;
+
+int sk_hubert_create(const SkHubertConfig* cfg, SkHubert** out);
+void sk_hubert_destroy(SkHubert* h);
+int64_t sk_hubert_param_count(const SkHubert* h);            /* fp32 elements of the flat weight buffer */
+int sk_hubert_tensor_info(const SkHubert* h, int idx, char* name_buf, int name_cap, int64_t* offset, int32_t* rows,
+                          int32_t* cols);                    /* idx < 0 -> number of tensors */
+int sk_hubert_frames(const SkHubert* h, int S);              /* frames produced for S-sample clips (after the pad) */
+int64_t sk_hubert_prepared_bytes(const SkHubert* h);         /* device scratch for the split (hi, lo) weight copies */
+int64_t sk_hubert_workspace_bytes(const SkHubert* h, int B, int S);
+int sk_hubert_bind(SkHubert* h, const float* weights, void* prepared, int64_t prepared_bytes, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+/* wav fp32 [B,S] (device), lens int64 [B] or NULL; ids int32 [B, sk_hubert_frames(S)] (all frames, untrimmed),
+ * n_frames int32 [B] = ceil(float32(lens)/S*T) (hubert_feature_extractor.py:46). */
+int sk_hubert_units(SkHubert* h, const float* wav, const int64_t* lens, int B, int S, int32_t* ids, int32_t* n_frames,
+                    void* stream);
+/* the fp32 layer-`n_layers` features [B*T, hidden] (parity checks against hidden_states[layer]) */
+int sk_hubert_features(SkHubert* h, const float* wav, int B, int S, float* feat, void* stream);
+/* Test hook: run the pass up to one stage and return that stage as fp32. stage 100+i = conv layer i output
+ * [B*T_i, conv_dim]; 200 = projection [B*T, hidden]; 201 = positional conv; 0..n_layers = hidden_states[stage]. */
+int sk_hubert_debug_stage(SkHubert* h, const float* wav, int B, int S, int stage, float* out, void* stream);
+/* Run-length dedup of each row's first n_frames[b] labels (UnitTokeniser.audio_represent,
+ * slamkit/tokeniser/unit_tokeniser.py:57): units/durations int32 [B,T], counts int32 [B]. */
+int sk_rle(const int32_t* ids, const int32_t* n_frames, int32_t* units, int32_t* durations, int32_t* counts, int B, int T,
+           void* stream);
+/* sklearn KMeans.predict tail (SK:cluster/_k_means_lloyd.pyx:198-213): labels = first argmin_j(sqnorm[j] - 2 dot[m][j]) */
+int sk_row_sqnorm(const float* x, float* out, int rows, int D, void* stream);
+int sk_kmeans_argmin(const float* dot, const float* centers_sqnorm, int32_t* labels, int M, int U, int ld, void* stream);
+/* conv0 statistics buffer length (doubles per clip) */
+int sk_conv0_nstat(void);
+
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 int64_t sk_launch_count(void);
 /* Bench-only device timing: when enabled, CUDA events are recorded on the launching stream around every launch of

@@ -246,6 +246,152 @@ attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, split-bf16 precision (HuBERT path): q/k/v/o are (hi, lo) bf16 pairs representing fp32-grade values;
+// S = Qh Kh^T + Qh Kl^T + Ql Kh^T and O = Ph Vh + Ph Vl + Pl Vh, all accumulated in fp32.  Bidirectional (the
+// reference passes no mask to HuBERT, hubert_feature_extractor.py:42), forward only.
+// ------------------------------------------------------------------------------------------------
+SK_DEVINL void acc_to_a_split(const float (&s)[8][4], uint32_t (&ph)[4][4], uint32_t (&pl)[4][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const float (&t)[4] = s[2 * kk + half];
+      const float h0 = bf16_round(t[0]), h1 = bf16_round(t[1]), h2 = bf16_round(t[2]), h3 = bf16_round(t[3]);
+      ph[kk][2 * half] = pack_bf16(h0, h1);
+      ph[kk][2 * half + 1] = pack_bf16(h2, h3);
+      pl[kk][2 * half] = pack_bf16(t[0] - h0, t[1] - h1);
+      pl[kk][2 * half + 1] = pack_bf16(t[2] - h2, t[3] - h3);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+attn_fwd_split_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_lo, const bf16* __restrict__ k_hi,
+                      const bf16* __restrict__ k_lo, const bf16* __restrict__ v_hi, const bf16* __restrict__ v_lo,
+                      bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, int T, int ld, int ldo, float scale) {
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  const uint32_t sQh = smem_u32(smem_attn);
+  const uint32_t sQl = sQh + 128 * 128;
+  const uint32_t sKV = sQl + 128 * 128;  // per stage: Kh, Kl, Vh, Vl (4 x 8 KB)
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int q0 = blockIdx.x * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t base = (size_t)b * T * ld + h * HD;
+  const float sl2 = scale * 1.4426950408889634f;
+  const int n_kv = (T + 63) / 64;
+
+  auto load_kv = [&](int j, int st) {
+    const uint32_t sb = sKV + st * 4 * 8192;
+    load_tile<64, 256>(sb, k_hi + base, ld, j * 64, T);
+    load_tile<64, 256>(sb + 8192, k_lo + base, ld, j * 64, T);
+    load_tile<64, 256>(sb + 2 * 8192, v_hi + base, ld, j * 64, T);
+    load_tile<64, 256>(sb + 3 * 8192, v_lo + base, ld, j * 64, T);
+  };
+  load_tile<128, 256>(sQh, q_hi + base, ld, q0, T);
+  load_tile<128, 256>(sQl, q_lo + base, ld, q0, T);
+  load_kv(0, 0);
+  cp_async_commit();
+
+  uint32_t qh[4][4], ql[4][4];
+  float oacc[8][4];
+  zero_acc(oacc);
+  float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
+  const int row_a = q0 + warp * 16 + (lane >> 2);
+
+  for (int j = 0; j < n_kv; ++j) {
+    const int st = j & 1;
+    if (j + 1 < n_kv) {
+      load_kv(j + 1, st ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (j == 0) {
+      load_a_frags(sQh, warp * 16, qh);
+      load_a_frags(sQl, warp * 16, ql);
+    }
+    const uint32_t sb = sKV + st * 4 * 8192;
+    float s[8][4];
+    zero_acc(s);
+    gemm_a_bT(s, ql, sb);          // Ql Kh^T (small terms first)
+    gemm_a_bT(s, qh, sb + 8192);   // Qh Kl^T
+    gemm_a_bT(s, qh, sb);          // Qh Kh^T
+    const int k0 = j * 64;
+    if (k0 + 64 > T) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (k0 + nt * 8 + (lane & 3) * 2 + (e & 1) >= T) s[nt][e] = -INFINITY;
+    }
+    float mx[2] = {m_i[0], m_i[1]};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float corr[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      corr[r] = (m_i[r] == -INFINITY) ? 0.f : exp2f((m_i[r] - mx[r]) * sl2);
+      m_i[r] = mx[r];
+    }
+    const float mb0 = mx[0] * sl2, mb1 = mx[1] * sl2;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] * sl2 - mb0);
+      s[nt][1] = exp2f(s[nt][1] * sl2 - mb0);
+      s[nt][2] = exp2f(s[nt][2] * sl2 - mb1);
+      s[nt][3] = exp2f(s[nt][3] * sl2 - mb1);
+      rs[0] += s[nt][0] + s[nt][1];
+      rs[1] += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_i[r] = l_i[r] * corr[r] + rs[r];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      oacc[nt][0] *= corr[0];
+      oacc[nt][1] *= corr[0];
+      oacc[nt][2] *= corr[1];
+      oacc[nt][3] *= corr[1];
+    }
+    uint32_t ph[4][4], pl[4][4];
+    acc_to_a_split(s, ph, pl);
+    gemm_p_b(oacc, pl, sb + 2 * 8192);  // Pl Vh
+    gemm_p_b(oacc, ph, sb + 3 * 8192);  // Ph Vl
+    gemm_p_b(oacc, ph, sb + 2 * 8192);  // Ph Vh
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
+    l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row_a + 8 * r;
+    if (row < T) {
+      const float inv = 1.0f / l_i[r];
+      const size_t off = ((size_t)b * T + row) * ldo + h * HD;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float v0 = oacc[nt][2 * r] * inv, v1 = oacc[nt][2 * r + 1] * inv;
+        const float h0 = bf16_round(v0), h1 = bf16_round(v1);
+        *reinterpret_cast<uint32_t*>(o_hi + off + nt * 8 + (lane & 3) * 2) = pack_bf16(h0, h1);
+        *reinterpret_cast<uint32_t*>(o_lo + off + nt * 8 + (lane & 3) * 2) = pack_bf16(v0 - h0, v1 - h1);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward preprocess: delta[b,h,t] = sum_d dO*O
 // ------------------------------------------------------------------------------------------------
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta,
@@ -509,6 +655,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
 constexpr int FWD_SMEM = 128 * 128 + 4 * 8192;        // 48 KB
 constexpr int DKDV_SMEM = 6 * 8192 + 2 * 2 * 64 * 4;  // 49 KB + stats
 constexpr int DQ_SMEM = 6 * 8192;
+constexpr int FWD_SPLIT_SMEM = 2 * 128 * 128 + 8 * 8192;  // 96 KB
 
 template <typename K>
 int set_smem(K kernel, int bytes) {
@@ -565,6 +712,24 @@ int sk_attn_bwd_launch(const bf16* q, const bf16* k, const bf16* v, const bf16* 
     SK_LAUNCH_CHECK();
     attn_bwd_dq_kernel<false><<<g2, 128, DQ_SMEM, s>>>(q, k, v, d_o, lse, delta, dq, T, ld, ldo, ldg, H, group, scale);
   }
+  sk_prof_end(s);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+
+// split-bf16 (hi, lo) bidirectional forward for the HuBERT encoder; all six inputs share the row pitch ld
+int sk_attn_fwd_split_launch(const bf16* q_hi, const bf16* q_lo, const bf16* k_hi, const bf16* k_lo, const bf16* v_hi,
+                             const bf16* v_lo, bf16* o_hi, bf16* o_lo, int B, int T, int H, int ld, int ldo, float scale,
+                             cudaStream_t s) {
+  SK_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "attention: leading dims must be multiples of 8");
+  static bool init = false;
+  if (!init) {
+    if (set_smem(attn_fwd_split_kernel, FWD_SPLIT_SMEM)) return -2;
+    init = true;
+  }
+  dim3 grid((T + 127) / 128, H, B);
+  sk_prof_begin(1, s);
+  attn_fwd_split_kernel<<<grid, 256, FWD_SPLIT_SMEM, s>>>(q_hi, q_lo, k_hi, k_lo, v_hi, v_lo, o_hi, o_lo, T, ld, ldo, scale);
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;

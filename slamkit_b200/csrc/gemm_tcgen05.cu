@@ -18,6 +18,8 @@
 #include <cudaTypedefs.h>
 #include <stdio.h>
 #include <mutex>
+#include <string.h>
+#include "kernels.h"
 
 namespace {
 
@@ -27,16 +29,23 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 
 struct GemmParams {
-  int M, N, K;
+  int M, N, K;          // M = rows per batch item when batch > 1
+  int batch;            // > 1: A is a 3-D tensor map (k, m, b) and C rows are b*M + m (conv layers, positional conv)
+  int a_mode;           // 0: A tile at (kb*64, m0[, b]);  1: shifted window (n_blk*64, m0 + kb, b) (grouped pos-conv)
+  int passes;           // 1, or 3 = split-bf16 (A_hi*B_hi + A_hi*B_lo + A_lo*B_hi): fp32-grade products on bf16 pipes
   void* C;
+  void* C_lo;           // non-null: write (hi, lo) bf16 pair, lo = bf16(v - hi)
   int ldc;
-  const bf16* bias;
+  const void* bias;
+  int bias_f32;         // bias is float (HuBERT path) instead of bf16
   const bf16* residual;
+  const bf16* residual_lo;
   int ldr;
   int tiles_m, tiles_n;
   int out_f32;          // 1: C is float
   int round_before_res; // 1: out = bf16(bf16(acc+bias) + res)  (matches an unfused bf16 linear followed by an add)
   int act;              // 0 none, 1 GELU(erf) applied to acc+bias
+  int col_gin, col_gout;  // > 0: output column c -> (c / col_gin) * col_gout + c % col_gin, dropped if c % col_gin >= col_gout
 };
 
 template <int BN>
@@ -55,7 +64,8 @@ SK_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo, GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -69,7 +79,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int tiles_per_batch = p.tiles_m * p.tiles_n;
+  const int num_tiles = tiles_per_batch * p.batch;
   const int num_kb = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -100,27 +111,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / p.tiles_n) * BM;
-        const int n0 = (t % p.tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + Cfg::A_BYTES;
-          const uint32_t fb = full_bar(stage);
-          mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
-          if (!A_MN) {
-            tma_load_2d(sA, &tmA, fb, kb * BK, m0);
-          } else {
+        const int bidx = t / tiles_per_batch;
+        const int r = t - bidx * tiles_per_batch;
+        const int m0 = (r / p.tiles_n) * BM;
+        const int n_blk = r % p.tiles_n;
+        const int n0 = n_blk * BN;
+        for (int pass = 0; pass < p.passes; ++pass) {
+          const CUtensorMap* mapA = (pass == 2) ? &tmA_lo : &tmA;
+          const CUtensorMap* mapB = (pass == 1) ? &tmB_lo : &tmB;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint32_t sB = sA + Cfg::A_BYTES;
+            const uint32_t fb = full_bar(stage);
+            mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+            if (!A_MN) {
+              if (p.a_mode & 2) {
+                if (p.a_mode & 1) tma_load_3d(sA, mapA, fb, n_blk * 64, m0 + kb, bidx);
+                else tma_load_3d(sA, mapA, fb, kb * BK, m0, bidx);
+              } else {
+                tma_load_2d(sA, mapA, fb, kb * BK, m0);
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), &tmA, fb, m0 + 64 * j, kb * BK);
-          }
-          if (!B_MN) {
-            tma_load_2d(sB, &tmB, fb, kb * BK, n0);
-          } else {
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), mapA, fb, m0 + 64 * j, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d(sB, mapB, fb, kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), &tmB, fb, n0 + 64 * j, kb * BK);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), mapB, fb, n0 + 64 * j, kb * BK);
+            }
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
           }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -136,7 +159,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int k_iters = num_kb * p.passes;
+        for (int kb = 0; kb < k_iters; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
@@ -163,12 +187,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / p.tiles_n) * BM;
-      const int n0 = (t % p.tiles_n) * BN;
+      const int bidx = t / tiles_per_batch;
+      const int rr = t - bidx * tiles_per_batch;
+      const int m0 = (rr / p.tiles_n) * BM;
+      const int n0 = (rr % p.tiles_n) * BN;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_in = m0 + q * 32 + lane;
+      const bool row_ok = row_in < p.M;
+      const size_t row = (size_t)bidx * p.M + row_in;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * Cfg::ACC_STRIDE);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -185,21 +212,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
               if (p.bias) {
-                const uint4 bv = ldg128(p.bias + col);
-                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                if (p.bias_f32) {
+                  const float* bp = reinterpret_cast<const float*>(p.bias) + col;
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                } else {
+                  const uint4 bv = ldg128(reinterpret_cast<const bf16*>(p.bias) + col);
+                  const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = unpack_bf16(bw[i]);
-                  v[2 * i] += f.x;
-                  v[2 * i + 1] += f.y;
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = unpack_bf16(bw[i]);
+                    v[2 * i] += f.x;
+                    v[2 * i + 1] += f.y;
+                  }
                 }
               }
               if (p.act == 1) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
               }
+              int ocol = col;
+              if (p.col_gin > 0) {
+                const int gi = col / p.col_gin, ci = col - gi * p.col_gin;
+                if (ci >= p.col_gout) continue;
+                ocol = gi * p.col_gout + ci;
+              }
               if (p.residual) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col);
+                const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + ocol);
                 const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -212,9 +253,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     v[2 * i + 1] += f.y;
                   }
                 }
+                if (p.residual_lo) {
+                  const uint4 lv = *reinterpret_cast<const uint4*>(p.residual_lo + row * p.ldr + ocol);
+                  const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = unpack_bf16(lw[i]);
+                    v[2 * i] += f.x;
+                    v[2 * i + 1] += f.y;
+                  }
+                }
               }
               if (p.out_f32) {
-                float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col;
+                float* dst = reinterpret_cast<float*>(p.C) + row * p.ldc + ocol;
                 *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
               } else {
@@ -223,7 +274,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 o.y = pack_bf16(v[2], v[3]);
                 o.z = pack_bf16(v[4], v[5]);
                 o.w = pack_bf16(v[6], v[7]);
-                stg128(reinterpret_cast<bf16*>(p.C) + (size_t)row * p.ldc + col, o);
+                stg128(reinterpret_cast<bf16*>(p.C) + row * p.ldc + ocol, o);
+                if (p.C_lo) {
+                  const float2 h0 = unpack_bf16(o.x), h1 = unpack_bf16(o.y), h2 = unpack_bf16(o.z), h3 = unpack_bf16(o.w);
+                  uint4 l;
+                  l.x = pack_bf16(v[0] - h0.x, v[1] - h0.y);
+                  l.y = pack_bf16(v[2] - h1.x, v[3] - h1.y);
+                  l.z = pack_bf16(v[4] - h2.x, v[5] - h2.y);
+                  l.w = pack_bf16(v[6] - h3.x, v[7] - h3.y);
+                  stg128(reinterpret_cast<bf16*>(p.C_lo) + row * p.ldc + ocol, l);
+                }
               }
             }
           }
@@ -283,10 +343,28 @@ int sk_make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t 
   return 0;
 }
 
+// 3-D variant (inner, rows with pitch row_stride, batch with pitch batch_stride; all in elements), box (64 x box_rows x 1)
+int sk_make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride,
+                    uint64_t batch_stride, uint32_t box_rows) {
+  std::call_once(g_encode_once, load_encode);
+  SK_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  SK_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  SK_REQUIRE((row_stride * 2) % 16 == 0 && (batch_stride * 2) % 16 == 0, "TMA strides must be multiples of 16 bytes");
+  cuuint64_t dims[3] = {inner, rows, batch};
+  cuuint64_t strides[2] = {row_stride * 2, batch_stride * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 namespace {
 
 template <int BN, bool A_MN, bool B_MN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -295,19 +373,18 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     attr_set = true;
   }
   sk_prof_begin(0, stream);
-  gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
   sk_prof_end(stream);
   SK_LAUNCH_CHECK();
   return 0;
 }
 
 template <int BN>
-int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
-                   cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, p, grid, s);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, p, grid, s);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tmA, tmB, p, grid, s);
-  return launch_gemm<BN, true, true>(tmA, tmB, p, grid, s);
+int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tm, p, grid, s);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tm, p, grid, s);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tm, p, grid, s);
+  return launch_gemm<BN, true, true>(tm, p, grid, s);
 }
 
 // Relative cost of one 128 x BN tile (BN=256 == 100), measured on B200 (profiles/r01_gemm_bench.txt): narrow tiles
@@ -335,41 +412,76 @@ int sk_pick_bn(int M, int N, int force_bn) {
   return best;
 }
 
-// The general entry point.  A: [M,K] (a_mn=0, lda = row pitch of the [M,K] array) or stored [K,M] (a_mn=1, lda = row
-// pitch of the [K,M] array).  B: [N,K] (b_mn=0) or stored [K,N] (b_mn=1).
+// General launcher (see SkGemmEx in kernels.h).
+int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
+  SK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0 && g.batch >= 1, "gemm: empty problem M=%d N=%d K=%d batch=%d", g.M, g.N, g.K,
+             g.batch);
+  SK_REQUIRE(g.N % 8 == 0, "gemm: N must be a multiple of 8 (N=%d)", g.N);
+  SK_REQUIRE(g.ldc % 8 == 0 && (g.residual == nullptr || g.ldr % 8 == 0), "gemm: ldc/ldr must be multiples of 8");
+  SK_REQUIRE((reinterpret_cast<uintptr_t>(g.C) & 15) == 0, "gemm: C must be 16-byte aligned");
+  SK_REQUIRE(g.passes == 1 || (g.passes == 3 && g.A_lo && g.B_lo), "gemm: passes must be 1, or 3 with lo operands");
+  const bool use3d = g.a_rows > 0;   // strided-window / batched A view
+  SK_REQUIRE(!use3d || !g.a_mn, "gemm: a batched / windowed A operand must be K-major");
+  SK_REQUIRE(g.a_mode == 0 || use3d, "gemm: a_mode 1 needs the 3-D A view");
+  const int BN = (g.a_mode == 1) ? 64 : sk_pick_bn(g.M * g.batch, g.N, g.force_bn);
+  CUtensorMap tm[4];
+  const void* As[2] = {g.A, g.passes == 3 ? g.A_lo : g.A};
+  const void* Bs[2] = {g.B, g.passes == 3 ? g.B_lo : g.B};
+  for (int i = 0; i < 2; ++i) {
+    int rc;
+    CUtensorMap* ta = &tm[i == 0 ? 0 : 2];
+    CUtensorMap* tb = &tm[i == 0 ? 1 : 3];
+    if (use3d) {
+      rc = sk_make_tmap_3d(ta, As[i], (uint64_t)g.a_inner, (uint64_t)g.a_rows, (uint64_t)g.batch, (uint64_t)g.a_row_stride,
+                           (uint64_t)g.a_batch_stride, BM);
+    } else if (!g.a_mn) {
+      rc = sk_make_tmap_2d(ta, As[i], 2, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, BK, BM);
+    } else {
+      rc = sk_make_tmap_2d(ta, As[i], 2, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 64, BK);
+    }
+    if (rc) return rc;
+    if (!g.b_mn) rc = sk_make_tmap_2d(tb, Bs[i], 2, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, BK, (uint32_t)BN);
+    else         rc = sk_make_tmap_2d(tb, Bs[i], 2, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 64, BK);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.batch = g.batch;
+  p.a_mode = (g.a_mode & 1) | (use3d ? 2 : 0);   // bit 1: A uses the 3-D TMA form
+  p.passes = g.passes;
+  p.C = g.C; p.C_lo = g.C_lo; p.ldc = g.ldc;
+  p.bias = g.bias; p.bias_f32 = g.bias_f32;
+  p.residual = reinterpret_cast<const bf16*>(g.residual);
+  p.residual_lo = reinterpret_cast<const bf16*>(g.residual_lo);
+  p.ldr = g.ldr;
+  p.tiles_m = (g.M + BM - 1) / BM;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  p.out_f32 = g.out_f32;
+  p.round_before_res = g.round_before_res;
+  p.act = g.act;
+  p.col_gin = g.col_gin; p.col_gout = g.col_gout;
+  const long tiles = (long)p.tiles_m * p.tiles_n * g.batch;
+  const int nsm = sk_num_sms();
+  const int grid = (int)(tiles < nsm ? tiles : nsm);
+  switch (BN) {
+    case 256: return dispatch_major<256>(g.a_mn, g.b_mn, tm, p, grid, stream);
+    case 128: return dispatch_major<128>(g.a_mn, g.b_mn, tm, p, grid, stream);
+    default:  return dispatch_major<64>(g.a_mn, g.b_mn, tm, p, grid, stream);
+  }
+}
+
+// Plain entry point.  A: [M,K] (a_mn=0, lda = row pitch of the [M,K] array) or stored [K,M] (a_mn=1, lda = row pitch of
+// the [K,M] array).  B: [N,K] (b_mn=0) or stored [K,N] (b_mn=1).
 int sk_gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                    int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
                    int force_bn, cudaStream_t stream) {
-  SK_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  SK_REQUIRE(N % 8 == 0, "gemm: N must be a multiple of 8 (N=%d)", N);
-  SK_REQUIRE(ldc % 8 == 0 && (residual == nullptr || ldr % 8 == 0), "gemm: ldc/ldr must be multiples of 8");
-  SK_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm: C must be 16-byte aligned");
-  const int BN = sk_pick_bn(M, N, force_bn);
-  CUtensorMap tmA, tmB;
-  int rc;
-  if (!a_mn) rc = sk_make_tmap_2d(&tmA, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
-  else       rc = sk_make_tmap_2d(&tmA, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
-  if (rc) return rc;
-  if (!b_mn) rc = sk_make_tmap_2d(&tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)BN);
-  else       rc = sk_make_tmap_2d(&tmB, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
-  if (rc) return rc;
-  GemmParams p;
-  p.M = M; p.N = N; p.K = K;
-  p.C = C; p.ldc = ldc;
-  p.bias = reinterpret_cast<const bf16*>(bias);
-  p.residual = reinterpret_cast<const bf16*>(residual);
-  p.ldr = ldr;
-  p.tiles_m = (M + BM - 1) / BM;
-  p.tiles_n = (N + BN - 1) / BN;
-  p.out_f32 = out_f32;
-  p.round_before_res = round_before_res;
-  p.act = act;
-  const int tiles = p.tiles_m * p.tiles_n;
-  const int nsm = sk_num_sms();
-  const int grid = tiles < nsm ? tiles : nsm;
-  switch (BN) {
-    case 256: return dispatch_major<256>(a_mn, b_mn, tmA, tmB, p, grid, stream);
-    case 128: return dispatch_major<128>(a_mn, b_mn, tmA, tmB, p, grid, stream);
-    default:  return dispatch_major<64>(a_mn, b_mn, tmA, tmB, p, grid, stream);
-  }
+  SkGemmEx g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.batch = 1; g.passes = 1;
+  g.A = A; g.lda = lda; g.a_mn = a_mn;
+  g.B = B; g.ldb = ldb; g.b_mn = b_mn;
+  g.C = C; g.ldc = ldc; g.out_f32 = out_f32;
+  g.bias = bias; g.residual = residual; g.ldr = ldr; g.round_before_res = round_before_res; g.act = act;
+  g.force_bn = force_bn;
+  return sk_gemm_ex_launch(g, stream);
 }

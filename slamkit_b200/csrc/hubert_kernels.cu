@@ -361,6 +361,11 @@ __global__ void rel_len_kernel(const int64_t* __restrict__ lens, int32_t* __rest
   n_frames[b] = v < 0 ? 0 : (v > T ? T : v);
 }
 
+__global__ void hilo_to_f32_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, float* __restrict__ out, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(hi[i]) + (lo ? __bfloat162float(lo[i]) : 0.f);
+}
+
 inline int grid_for(long work_items, int threads, int max_blocks_per_sm = 16) {
   long b = (work_items + threads - 1) / threads;
   const long cap = (long)sk_num_sms() * max_blocks_per_sm;
@@ -437,6 +442,11 @@ int sk_rle_launch(const int32_t* labels, const int32_t* n_frames, int32_t* units
 }
 int sk_rel_len_launch(const int64_t* lens, int32_t* n_frames, int B, int S, int T, cudaStream_t s) {
   rel_len_kernel<<<(B + 127) / 128, 128, 0, s>>>(lens, n_frames, B, S, T);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_hilo_to_f32_launch(const bf16* hi, const bf16* lo, float* out, long n, cudaStream_t s) {
+  hilo_to_f32_kernel<<<grid_for(n, 256), 256, 0, s>>>(hi, lo, out, n);
   SK_LAUNCH_CHECK();
   return 0;
 }

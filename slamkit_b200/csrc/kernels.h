@@ -6,7 +6,31 @@
 // gemm_tcgen05.cu
 int sk_make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld,
                     uint32_t box_inner, uint32_t box_outer);
+int sk_make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride,
+                    uint64_t batch_stride, uint32_t box_rows);
 int sk_pick_bn(int M, int N, int force_bn);
+// Extended GEMM description (HuBERT path): batched / strided-window A operands (convolutions as GEMMs without an
+// im2col copy), split-bf16 3-pass accumulation, fp32 bias, hi/lo residual and outputs, grouped column compaction.
+struct SkGemmEx {
+  int M, N, K;              // M: rows per batch item
+  int batch;                // >= 1
+  int a_mode;               // 0 plain, 1 shifted-window grouped conv (BN = 64 = one channel group per N tile)
+  int passes;               // 1 or 3
+  const void *A, *A_lo;
+  int lda, a_mn;
+  long a_inner, a_rows, a_row_stride, a_batch_stride;   // 3-D A view (elements), active when a_rows > 0
+  const void *B, *B_lo;
+  int ldb, b_mn;
+  void *C, *C_lo;
+  int ldc, out_f32;
+  const void* bias;
+  int bias_f32;
+  const void *residual, *residual_lo;
+  int ldr, round_before_res, act;
+  int col_gin, col_gout;
+  int force_bn;
+};
+int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream);
 int sk_gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                    int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
                    int force_bn, cudaStream_t stream);
@@ -41,6 +65,9 @@ int sk_attn_fwd_launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, flo
 int sk_attn_bwd_launch(const bf16* q, const bf16* k, const bf16* v, const bf16* o, const bf16* d_o, const float* lse,
                        float* delta, bf16* dq, bf16* dk, bf16* dv, int B, int T, int H, int KVH, int ld, int ldo,
                        int ldg, int causal, float scale, cudaStream_t s);
+int sk_attn_fwd_split_launch(const bf16* q_hi, const bf16* q_lo, const bf16* k_hi, const bf16* k_lo, const bf16* v_hi,
+                             const bf16* v_lo, bf16* o_hi, bf16* o_lo, int B, int T, int H, int ld, int ldo, float scale,
+                             cudaStream_t s);
 
 // hubert_kernels.cu
 int sk_split_f32_launch(const float* x, bf16* hi, bf16* lo, long n, cudaStream_t s);
@@ -58,3 +85,4 @@ int sk_kmeans_argmin_launch(const float* dot, const float* csq, int32_t* labels,
 int sk_rle_launch(const int32_t* labels, const int32_t* n_frames, int32_t* units, int32_t* durations, int32_t* counts,
                   int B, int T, cudaStream_t s);
 int sk_rel_len_launch(const int64_t* lens, int32_t* n_frames, int B, int S, int T, cudaStream_t s);
+int sk_hilo_to_f32_launch(const bf16* hi, const bf16* lo, float* out, long n, cudaStream_t s);
