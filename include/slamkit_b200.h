@@ -40,6 +40,13 @@ int sk_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const vo
                  int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
                  int force_bn, void* stream);
 
+/* Same GEMM with a caller-provided fp32 scratch: when the output has few tiles and K is long (weight gradients
+ * dW = dY^T X with K = tokens) the K loop is split over idle SMs into fp32 slabs that are reduced in a fixed order
+ * (deterministic).  accumulate=1 adds into C (gradient accumulation).  Falls back to the plain kernel when the shape
+ * does not benefit or the scratch is too small. */
+int sk_gemm_bf16_splitk(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                        int ldc, int accumulate, void* splitk_ws, int64_t splitk_ws_bytes, void* stream);
+
 /* ---- causal-LM element-wise / reduction kernels (path (ii)) --------------------------------------------------- */
 /* Embedding lookup, HF:models/qwen2/modeling_qwen2.py:332-415 (embed_tokens). ids int64 [M]. */
 int sk_embed_fwd(const int64_t* ids, const void* table, void* out, int M, int D, int V, void* stream);

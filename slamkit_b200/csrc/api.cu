@@ -101,6 +101,12 @@ int sk_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const vo
   return sk_gemm_launch(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, out_f32, bias, residual, ldr, round_before_res, act,
                         force_bn, S(stream));
 }
+int sk_gemm_bf16_splitk(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                        int ldc, int accumulate, void* splitk_ws, int64_t splitk_ws_bytes, void* stream) {
+  SK_REQUIRE(A && B && C, "sk_gemm_bf16_splitk: null operand");
+  return sk_gemm_launch(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, 0, nullptr, accumulate ? C : nullptr, ldc, 1, 0, 0,
+                        S(stream), splitk_ws, (size_t)splitk_ws_bytes);
+}
 int sk_embed_fwd(const int64_t* ids, const void* table, void* out, int M, int D, int V, void* stream) {
   return sk_embed_fwd_launch(ids, CBF(table), BF(out), M, D, V, S(stream));
 }

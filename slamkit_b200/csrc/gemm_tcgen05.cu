@@ -46,6 +46,8 @@ struct GemmParams {
   int round_before_res; // 1: out = bf16(bf16(acc+bias) + res)  (matches an unfused bf16 linear followed by an add)
   int act;              // 0 none, 1 GELU(erf) applied to acc+bias
   int col_gin, col_gout;  // > 0: output column c -> (c / col_gin) * col_gout + c % col_gin, dropped if c % col_gin >= col_gout
+  int splits;           // > 1: split-K; work item = (tile, split), fp32 partial tiles go to splitk_ws[split][M][N]
+  float* splitk_ws;
 };
 
 template <int BN>
@@ -80,8 +82,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
-  const int num_tiles = tiles_per_batch * p.batch;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_tiles = tiles_per_batch * p.batch * p.splits;   // work items
+  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int kb_per_split = (num_kb_total + p.splits - 1) / p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -111,15 +114,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int bidx = t / tiles_per_batch;
-        const int r = t - bidx * tiles_per_batch;
+        const int split = t % p.splits;
+        const int tt = t / p.splits;
+        const int bidx = tt / tiles_per_batch;
+        const int r = tt - bidx * tiles_per_batch;
         const int m0 = (r / p.tiles_n) * BM;
         const int n_blk = r % p.tiles_n;
         const int n0 = n_blk * BN;
+        const int kb_begin = split * kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
         for (int pass = 0; pass < p.passes; ++pass) {
           const CUtensorMap* mapA = (pass == 2) ? &tmA_lo : &tmA;
           const CUtensorMap* mapB = (pass == 1) ? &tmB_lo : &tmB;
-          for (int kb = 0; kb < num_kb; ++kb) {
+          for (int kb = kb_begin; kb < kb_end; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sB = sA + Cfg::A_BYTES;
@@ -159,7 +166,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
-        const int k_iters = num_kb * p.passes;
+        const int split = t % p.splits;
+        const int kb_begin = split * kb_per_split;
+        const int kb_cnt = max(0, min(num_kb_total, kb_begin + kb_per_split) - kb_begin);
+        const int k_iters = kb_cnt * p.passes;
         for (int kb = 0; kb < k_iters; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -187,8 +197,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int bidx = t / tiles_per_batch;
-      const int rr = t - bidx * tiles_per_batch;
+      const int split = t % p.splits;
+      const int tt = t / p.splits;
+      const int bidx = tt / tiles_per_batch;
+      const int rr = tt - bidx * tiles_per_batch;
       const int m0 = (rr / p.tiles_n) * BM;
       const int n0 = (rr % p.tiles_n) * BN;
       mbar_wait(tfull_bar(as), aphase);
@@ -211,6 +223,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+              if (p.splits > 1) {
+                float* dst = p.splitk_ws + ((size_t)split * p.M + row_in) * p.N + col;
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                continue;
+              }
               if (p.bias) {
                 if (p.bias_f32) {
                   const float* bp = reinterpret_cast<const float*>(p.bias) + col;
@@ -302,6 +320,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// C[m,n] = bf16( sum_s ws[s][m][n] ) (+ C when accumulate), fixed summation order -> deterministic split-K
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, bf16* __restrict__ C, int M, int N, int ldc, int splits,
+                                     int accumulate) {
+  const long total = (long)M * N / 8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long e = i * 8;
+    const int m = (int)(e / N), n = (int)(e % N);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < splits; ++s) {
+      const float* src = ws + ((size_t)s * M + m) * N + n;
+      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    bf16* dst = C + (size_t)m * ldc + n;
+    if (accumulate) {
+      const uint4 o = *reinterpret_cast<const uint4*>(dst);
+      const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16(ow[k]);
+        acc[2 * k] = bf16_round(acc[2 * k]) + f.x;
+        acc[2 * k + 1] = bf16_round(acc[2 * k + 1]) + f.y;
+      }
+    }
+    stg128(dst, make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                           pack_bf16(acc[6], acc[7])));
   }
 }
 
@@ -462,19 +510,54 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
   p.col_gin = g.col_gin; p.col_gout = g.col_gout;
   const long tiles = (long)p.tiles_m * p.tiles_n * g.batch;
   const int nsm = sk_num_sms();
-  const int grid = (int)(tiles < nsm ? tiles : nsm);
-  switch (BN) {
-    case 256: return dispatch_major<256>(g.a_mn, g.b_mn, tm, p, grid, stream);
-    case 128: return dispatch_major<128>(g.a_mn, g.b_mn, tm, p, grid, stream);
-    default:  return dispatch_major<64>(g.a_mn, g.b_mn, tm, p, grid, stream);
+  // split-K: only for plain bf16-output GEMMs that leave most SMs idle and have a long K loop (the small wgrads)
+  p.splits = 1;
+  p.splitk_ws = nullptr;
+  const int num_kb = (g.K + BK - 1) / BK;
+  if (g.splitk_ws && g.batch == 1 && g.passes == 1 && !g.out_f32 && !g.bias && !g.act && !g.C_lo && g.col_gin == 0 &&
+      tiles * 2 <= nsm && num_kb >= 16) {
+    int sp = (int)(nsm / tiles);
+    if (sp > 8) sp = 8;
+    if (sp > num_kb / 4) sp = num_kb / 4;
+    if ((size_t)sp * g.M * g.N * sizeof(float) > g.splitk_ws_bytes) sp = (int)(g.splitk_ws_bytes / ((size_t)g.M * g.N * sizeof(float)));
+    if (sp >= 2) {
+      const int per = (num_kb + sp - 1) / sp;
+      sp = (num_kb + per - 1) / per;   // no empty split: every work item issues at least one MMA
+    }
+    if (sp >= 2) {
+      p.splits = sp;
+      p.splitk_ws = reinterpret_cast<float*>(g.splitk_ws);
+    }
   }
+  const long work = tiles * p.splits;
+  const int grid = (int)(work < nsm ? work : nsm);
+  int rc;
+  switch (BN) {
+    case 256: rc = dispatch_major<256>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
+    case 128: rc = dispatch_major<128>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
+    default:  rc = dispatch_major<64>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
+  }
+  if (rc) return rc;
+  if (p.splits > 1) {
+    // residual == C means "accumulate into C" (gradient accumulation); any other residual is not supported here
+    SK_REQUIRE(g.residual == nullptr || g.residual == g.C, "gemm: split-K supports only in-place accumulation");
+    const long n8 = (long)g.M * g.N / 8;
+    int blocks = (int)((n8 + 255) / 256);
+    if (blocks > nsm * 8) blocks = nsm * 8;
+    sk_prof_begin(0, stream);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.splitk_ws, reinterpret_cast<bf16*>(g.C), g.M, g.N, g.ldc, p.splits,
+                                                     g.residual != nullptr);
+    sk_prof_end(stream);
+    SK_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 // Plain entry point.  A: [M,K] (a_mn=0, lda = row pitch of the [M,K] array) or stored [K,M] (a_mn=1, lda = row pitch of
 // the [K,M] array).  B: [N,K] (b_mn=0) or stored [K,N] (b_mn=1).
 int sk_gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                    int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
-                   int force_bn, cudaStream_t stream) {
+                   int force_bn, cudaStream_t stream, void* splitk_ws, size_t splitk_ws_bytes) {
   SkGemmEx g;
   memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K; g.batch = 1; g.passes = 1;
@@ -483,5 +566,7 @@ int sk_gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const 
   g.C = C; g.ldc = ldc; g.out_f32 = out_f32;
   g.bias = bias; g.residual = residual; g.ldr = ldr; g.round_before_res = round_before_res; g.act = act;
   g.force_bn = force_bn;
+  g.splitk_ws = splitk_ws;
+  g.splitk_ws_bytes = splitk_ws_bytes;
   return sk_gemm_ex_launch(g, stream);
 }

@@ -29,11 +29,13 @@ struct SkGemmEx {
   int ldr, round_before_res, act;
   int col_gin, col_gout;
   int force_bn;
+  void* splitk_ws;          // optional fp32 scratch enabling deterministic split-K for small-output / long-K GEMMs
+  size_t splitk_ws_bytes;
 };
 int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream);
 int sk_gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                    int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
-                   int force_bn, cudaStream_t stream);
+                   int force_bn, cudaStream_t stream, void* splitk_ws = nullptr, size_t splitk_ws_bytes = 0);
 
 // lm_kernels.cu
 int sk_embed_fwd_launch(const int64_t* ids, const bf16* E, bf16* out, int M, int D, int V, cudaStream_t s);

@@ -27,7 +27,7 @@ struct WsLayout {
   int64_t X, h1, rstd1, qkv, ao, lse, xmid, h2, rstd2, gu, act;  // per-layer strides below
   int64_t sX, sh, srstd, sqkv, slse, sgu, sact;
   int64_t hf, rstdf, logits, dlogits, dxA, dxB, dh, dao, dqkv, dact, dgu, delta;
-  int64_t dw_partial, colsum_partial, ce_partial, embed_scratch, total;
+  int64_t dw_partial, colsum_partial, ce_partial, embed_scratch, splitk, splitk_bytes, total;
 };
 }  // namespace
 
@@ -107,6 +107,8 @@ WsLayout make_layout(const SkLm* lm, int B, int T) {
   w.colsum_partial = take((int64_t)sk_colsum_splits() * lm->qkv_dim * 4);
   w.ce_partial = take((int64_t)sk_ce_blocks((int)M) * 2 * 4);
   w.embed_scratch = take((int64_t)lm->Vp * lm->d * 4);
+  w.splitk_bytes = (int64_t)8 * lm->qkv_dim * lm->d * 4;   // up to 8 fp32 slabs of the largest split-K wgrad
+  w.splitk = take(w.splitk_bytes);
   w.total = cur;
   return w;
 }
@@ -132,8 +134,10 @@ int linear_dgrad(int M, int N, int K, const bf16* dy, const bf16* W, bf16* dx, c
   return sk_gemm_launch(M, K, N, dy, N, 0, W, K, 1, dx, K, 0, nullptr, nullptr, 0, 0, 0, 0, s);
 }
 // dW[N,K] (+)= dy[M,N]^T * x[M,K]
-int linear_wgrad(int M, int N, int K, const bf16* dy, const bf16* x, bf16* dW, int accumulate, cudaStream_t s) {
-  return sk_gemm_launch(N, K, M, dy, N, 1, x, K, 1, dW, K, 0, nullptr, accumulate ? dW : nullptr, K, 1, 0, 0, s);
+int linear_wgrad(int M, int N, int K, const bf16* dy, const bf16* x, bf16* dW, int accumulate, cudaStream_t s,
+                 void* splitk_ws, size_t splitk_bytes) {
+  return sk_gemm_launch(N, K, M, dy, N, 1, x, K, 1, dW, K, 0, nullptr, accumulate ? dW : nullptr, K, 1, 0, 0, s,
+                        splitk_ws, splitk_bytes);
 }
 
 int check_bound(const SkLm* lm, int B, int T, const WsLayout& w) {
@@ -211,7 +215,7 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
 
   // lm_head
   SK_TRY(linear_dgrad(M, lm->Vp, d, dlogits, P + lm->off_head, dh, s));
-  SK_TRY(linear_wgrad(M, lm->Vp, d, dlogits, hf, G + lm->off_head, accumulate, s));
+  SK_TRY(linear_wgrad(M, lm->Vp, d, dlogits, hf, G + lm->off_head, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
   SK_TRY(sk_rmsnorm_bwd_launch(dh, wsp<bf16>(lm, w.X + w.sX * L), P + lm->off_final_norm, wsp<float>(lm, w.rstdf),
                                nullptr, dxA, G + lm->off_final_norm, dwp, M, d, accumulate, s));
   for (int l = L - 1; l >= 0; --l) {
@@ -230,14 +234,14 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
 
     // MLP
     SK_TRY(linear_dgrad(M, d, F, dxA, P + o.wd, dact, s));
-    SK_TRY(linear_wgrad(M, d, F, dxA, act, G + o.wd, accumulate, s));
+    SK_TRY(linear_wgrad(M, d, F, dxA, act, G + o.wd, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
     SK_TRY(sk_swiglu_bwd_launch(gu, dact, dgu, M, F, s));
     SK_TRY(linear_dgrad(M, 2 * F, d, dgu, P + o.wgu, dh, s));
-    SK_TRY(linear_wgrad(M, 2 * F, d, dgu, h2, G + o.wgu, accumulate, s));
+    SK_TRY(linear_wgrad(M, 2 * F, d, dgu, h2, G + o.wgu, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
     SK_TRY(sk_rmsnorm_bwd_launch(dh, xmid, P + o.ln2, r2, dxA, dxB, G + o.ln2, dwp, M, d, accumulate, s));
     // attention
     SK_TRY(linear_dgrad(M, d, d, dxB, P + o.wo, dao, s));
-    SK_TRY(linear_wgrad(M, d, d, dxB, ao, G + o.wo, accumulate, s));
+    SK_TRY(linear_wgrad(M, d, d, dxB, ao, G + o.wo, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
     SK_TRY(sk_attn_bwd_launch(qkv, qkv + lm->H * lm->hd, qkv + (lm->H + lm->KVH) * lm->hd, ao, dao, lse,
                               wsp<float>(lm, w.delta), dqkv, dqkv + lm->H * lm->hd, dqkv + (lm->H + lm->KVH) * lm->hd, B,
                               T, lm->H, lm->KVH, Q, d, Q, 1, scale, s));
@@ -245,7 +249,7 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
     if (lm->cfg.qkv_bias)
       SK_TRY(sk_colsum_launch(dqkv, G + o.bqkv, wsp<float>(lm, w.colsum_partial), M, Q, Q, accumulate, s));
     SK_TRY(linear_dgrad(M, Q, d, dqkv, P + o.wqkv, dh, s));
-    SK_TRY(linear_wgrad(M, Q, d, dqkv, h1, G + o.wqkv, accumulate, s));
+    SK_TRY(linear_wgrad(M, Q, d, dqkv, h1, G + o.wqkv, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
     SK_TRY(sk_rmsnorm_bwd_launch(dh, x, P + o.ln1, r1, dxB, dxA, G + o.ln1, dwp, M, d, accumulate, s));
   }
   // embedding: tied -> add on top of the lm_head gradient just written; untied -> honour `accumulate`

@@ -40,6 +40,18 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+def gemm_splitk(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bool, b_mn: bool, accumulate: bool,
+                ws_bytes: int = 64 << 20) -> torch.Tensor:
+    """Weight-gradient style GEMM with deterministic split-K (sk_gemm_bf16_splitk)."""
+    lib = L.require_cuda()
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N = b.shape[1] if b_mn else b.shape[0]
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    L.check(lib.sk_gemm_bf16_splitk(M, N, K, L.ptr(a), a.stride(0), int(a_mn), L.ptr(b), b.stride(0), int(b_mn), L.ptr(out),
+                                    out.stride(0), int(accumulate), L.ptr(ws), C.c_int64(ws_bytes), L.stream_ptr()))
+    return out
+
+
 def embed_fwd(ids: torch.Tensor, table: torch.Tensor, vocab: int) -> torch.Tensor:
     lib = L.require_cuda()
     M, D = ids.numel(), table.shape[1]

@@ -68,6 +68,23 @@ def test_gemm_epilogues():
     assert rel_err(c.cpu(), acc.to(torch.bfloat16).float() + res.float()) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,acc", [(1152, 896, 8192, False), (896, 896, 8192, True), (512, 896, 8192, False),
+                                         (384, 264, 2120, True)])
+def test_gemm_splitk_wgrad(M, N, K, acc):
+    """dW[M,N] (+)= dY[K,M]^T X[K,N] with the K (= tokens) loop split over idle SMs; deterministic."""
+    from slamkit_b200 import ops
+    dy, x = _randn(K, M, seed=11), _randn(K, N, seed=12)
+    ref = dy.float().t() @ x.float()
+    base = _randn(M, N, seed=13, scale=5.0)
+    out = base.clone().to(DEV)
+    ops.gemm_splitk(dy.to(DEV), x.to(DEV), out, a_mn=True, b_mn=True, accumulate=acc)
+    want = ref.to(torch.bfloat16).float() + base.float() if acc else ref
+    assert rel_err(out.cpu(), want) < 4e-3, rel_err(out.cpu(), want)
+    out2 = base.clone().to(DEV)
+    ops.gemm_splitk(dy.to(DEV), x.to(DEV), out2, a_mn=True, b_mn=True, accumulate=acc)
+    assert torch.equal(out, out2)
+
+
 def test_gemm_rejects_bad_arguments():
     from slamkit_b200 import ops, _lib
     a, b = _randn(64, 64).to(DEV), _randn(60, 64).to(DEV)  # N=60 is not a multiple of 8
