@@ -118,7 +118,7 @@ SK_DEVINL void zero_acc(float (&a)[8][4]) {
 // forward: BR = 128 query rows per CTA (8 warps x 16 rows), BC = 64 keys per step
 // ------------------------------------------------------------------------------------------------
 template <bool CAUSAL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, bf16* __restrict__ o,
                 float* __restrict__ lse, int T, int ld, int ldo, int H, int group, float scale) {
   extern __shared__ __align__(128) uint8_t smem_attn[];

@@ -48,6 +48,7 @@ struct GemmParams {
   int col_gin, col_gout;  // > 0: output column c -> (c / col_gin) * col_gout + c % col_gin, dropped if c % col_gin >= col_gout
   int splits;           // > 1: split-K; work item = (tile, split), fp32 partial tiles go to splitk_ws[split][M][N]
   float* splitk_ws;
+  int tma_store;        // 1: bf16 output leaves through swizzled smem staging + cp.async.bulk.tensor stores (tmC)
 };
 
 template <int BN>
@@ -58,8 +59,9 @@ struct GemmCfg {
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int STAGING_BYTES = 4 * 2 * 4096;  // per epilogue warp: 2 x (32 rows x 128 B) TMA-store buffers
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 };
 
 SK_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -67,11 +69,13 @@ SK_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo, GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo,
+                    const __grid_constant__ CUtensorMap tmC, GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t staging_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;   // 1024-byte aligned
+  const uint32_t bar_base = staging_base + Cfg::STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
@@ -196,6 +200,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t store_cnt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int split = t % p.splits;
       const int tt = t / p.splits;
@@ -209,6 +214,79 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool row_ok = row_in < p.M;
       const size_t row = (size_t)bidx * p.M + row_in;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * Cfg::ACC_STRIDE);
+      if (p.tma_store) {
+        // coalesced path: TMEM -> registers -> 128B-swizzled smem (this warp's private 32-row buffer) -> TMA store
+#pragma unroll 1
+        for (int c2 = 0; c2 < BN / 64; ++c2) {
+          const uint32_t sbuf = staging_base + (uint32_t)(warp - 2) * 8192u + (store_cnt & 1u) * 4096u;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c2 * 64 + half * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = n0 + c2 * 64 + half * 32 + g * 8;
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+              if (col < p.N) {
+                if (p.bias) {
+                  if (p.bias_f32) {
+                    const float* bp = reinterpret_cast<const float*>(p.bias) + col;
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                  } else {
+                    const uint4 bv = ldg128(reinterpret_cast<const bf16*>(p.bias) + col);
+                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const float2 f = unpack_bf16(bw[i]);
+                      v[2 * i] += f.x;
+                      v[2 * i + 1] += f.y;
+                    }
+                  }
+                }
+                if (p.act == 1) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+                }
+                if (p.residual && row_ok) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col);
+                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = unpack_bf16(rw[i]);
+                    if (p.round_before_res) {
+                      v[2 * i] = bf16_round(v[2 * i]) + f.x;
+                      v[2 * i + 1] = bf16_round(v[2 * i + 1]) + f.y;
+                    } else {
+                      v[2 * i] += f.x;
+                      v[2 * i + 1] += f.y;
+                    }
+                  }
+                }
+              }
+              const int j = half * 4 + g;
+              const uint32_t dst = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16(v[0], v[1])),
+                           "r"(pack_bf16(v[2], v[3])), "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7]))
+                           : "memory");
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, sbuf, n0 + c2 * 64, m0 + q * 32);
+            tma_store_commit();
+          }
+          ++store_cnt;
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -313,6 +391,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
+    if (p.tma_store && lane == 0) tma_store_wait<0>();   // all bulk stores retired before the CTA exits
   }
 
   tc_fence_before();
@@ -421,7 +500,7 @@ int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream
     attr_set = true;
   }
   sk_prof_begin(0, stream);
-  gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+  gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
   sk_prof_end(stream);
   SK_LAUNCH_CHECK();
   return 0;
@@ -452,7 +531,8 @@ int sk_pick_bn(int M, int N, int force_bn) {
     const long tiles = (long)((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     const long waves = (tiles + nsm - 1) / nsm;
     const long cost = waves * tile_cost(bn);
-    if (best_cost < 0 || cost < best_cost) {
+    // a narrower tile has to be clearly better (>= 15 %) to displace a wider one: measured ties favour BN = 256
+    if (best_cost < 0 || cost * 100 < best_cost * 85) {
       best_cost = cost;
       best = bn;
     }
@@ -472,7 +552,7 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
   SK_REQUIRE(!use3d || !g.a_mn, "gemm: a batched / windowed A operand must be K-major");
   SK_REQUIRE(g.a_mode == 0 || use3d, "gemm: a_mode 1 needs the 3-D A view");
   const int BN = (g.a_mode == 1) ? 64 : sk_pick_bn(g.M * g.batch, g.N, g.force_bn);
-  CUtensorMap tm[4];
+  CUtensorMap tm[5];
   const void* As[2] = {g.A, g.passes == 3 ? g.A_lo : g.A};
   const void* Bs[2] = {g.B, g.passes == 3 ? g.B_lo : g.B};
   for (int i = 0; i < 2; ++i) {
@@ -528,6 +608,14 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
       p.splits = sp;
       p.splitk_ws = reinterpret_cast<float*>(g.splitk_ws);
     }
+  }
+  // TMA-store epilogue for the plain bf16 outputs (everything on the LM path)
+  p.tma_store = 0;
+  tm[4] = tm[0];
+  if (!g.out_f32 && !g.C_lo && g.col_gin == 0 && p.splits == 1 && g.batch == 1 && !use3d && (g.ldc * 2) % 16 == 0) {
+    const int rc2 = sk_make_tmap_2d(&tm[4], g.C, 2, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc, 64, 32);
+    if (rc2) return rc2;
+    p.tma_store = 1;
   }
   const long work = tiles * p.splits;
   const int grid = (int)(work < nsm ? work : nsm);

@@ -124,7 +124,7 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16*
 // backward: g = dy*w ; xhat = x*rstd ; dx = rstd*(g - xhat*mean(g*xhat)) (+ dres) ; dw partial = sum_rows dy*bf16(xhat)
 // grid-stride over rows so every block owns a fixed slice; per-block partial dw rows are written to `dw_partial`
 // [gridDim.x, D] and reduced by rmsnorm_dw_reduce_kernel in a fixed order (deterministic).
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2)
 rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                    const float* __restrict__ rstd_in, const bf16* __restrict__ dres, bf16* __restrict__ dx,
                    float* __restrict__ dw_partial, int M, int D) {
@@ -144,16 +144,16 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
   }
   for (int row = blockIdx.x * WARPS_PER_BLOCK + warp; row < M; row += gridDim.x * WARPS_PER_BLOCK) {
     const float rstd = rstd_in[row];
-    float g[MAX_VEC_PER_LANE][8], xh[MAX_VEC_PER_LANE][8];
+    uint4 xq[MAX_VEC_PER_LANE], dq[MAX_VEC_PER_LANE];   // packed bf16: kept raw to stay under 96 registers
     float dot = 0.f;
 #pragma unroll
     for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
       const int c = lane + 32 * j;
       if (c < nvec) {
-        const uint4 xv = ldg128_stream(x + (size_t)row * D + c * 8);
-        const uint4 dv = ldg128_stream(dy + (size_t)row * D + c * 8);
-        const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
-        const uint32_t du[4] = {dv.x, dv.y, dv.z, dv.w};
+        xq[j] = ldg128_stream(x + (size_t)row * D + c * 8);
+        dq[j] = ldg128_stream(dy + (size_t)row * D + c * 8);
+        const uint32_t xu[4] = {xq[j].x, xq[j].y, xq[j].z, xq[j].w};
+        const uint32_t du[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
         const uint32_t wu[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -161,11 +161,7 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
           const float2 df = unpack_bf16(du[k]);
           const float2 wf = unpack_bf16(wu[k]);
           const float xh0 = xf.x * rstd, xh1 = xf.y * rstd;
-          xh[j][2 * k] = xh0;
-          xh[j][2 * k + 1] = xh1;
-          g[j][2 * k] = bf16_round(df.x * wf.x);
-          g[j][2 * k + 1] = bf16_round(df.y * wf.y);
-          dot += g[j][2 * k] * xh0 + g[j][2 * k + 1] * xh1;
+          dot += bf16_round(df.x * wf.x) * xh0 + bf16_round(df.y * wf.y) * xh1;
           dwacc[j][2 * k] += df.x * bf16_round(xh0);
           dwacc[j][2 * k + 1] += df.y * bf16_round(xh1);
         }
@@ -176,9 +172,18 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
     for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
       const int c = lane + 32 * j;
       if (c < nvec) {
+        const uint32_t xu[4] = {xq[j].x, xq[j].y, xq[j].z, xq[j].w};
+        const uint32_t du[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
+        const uint32_t wu[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
         float o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = rstd * (g[j][k] - xh[j][k] * dot);
+        for (int k = 0; k < 4; ++k) {
+          const float2 xf = unpack_bf16(xu[k]);
+          const float2 df = unpack_bf16(du[k]);
+          const float2 wf = unpack_bf16(wu[k]);
+          o[2 * k] = rstd * (bf16_round(df.x * wf.x) - xf.x * rstd * dot);
+          o[2 * k + 1] = rstd * (bf16_round(df.y * wf.y) - xf.y * rstd * dot);
+        }
         if (dres) {
           const uint4 rv = ldg128_stream(dres + (size_t)row * D + c * 8);
           const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
@@ -212,15 +217,25 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
   }
 }
 
-// out[j] = bf16( (accumulate ? out[j] : 0) + sum_b partial[b][j] )
-__global__ void colsum_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int nblocks, int D,
-                                     int accumulate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= D) return;
+// out[j] = bf16( (accumulate ? out[j] : 0) + sum_b partial[b][j] ).  Block = 32 columns x 8 row groups; rows are
+// summed in a fixed order (deterministic), 128-byte coalesced reads per warp.
+__global__ void __launch_bounds__(256)
+colsum_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int nblocks, int D, int accumulate) {
+  __shared__ float sred[8][33];
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + c;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * D + j];
-  if (accumulate) s += __bfloat162float(out[j]);
-  out[j] = __float2bfloat16_rn(s);
+  if (j < D)
+    for (int b = rg; b < nblocks; b += 8) s += partial[(size_t)b * D + j];
+  sred[rg][c] = s;
+  __syncthreads();
+  if (rg == 0 && j < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sred[r][c];
+    if (accumulate) t += __bfloat162float(out[j]);
+    out[j] = __float2bfloat16_rn(t);
+  }
 }
 
 // column sums of a bf16 [M, N] matrix (leading dim ld) -> partial[gridDim.y][N]; used for the q/k/v bias gradient
@@ -623,7 +638,7 @@ int sk_rmsnorm_fwd_launch(const bf16* x, const bf16* w, bf16* y, float* rstd, in
   return 0;
 }
 // dw_partial must hold sk_rmsnorm_bwd_blocks() * D floats
-extern "C" int sk_rmsnorm_bwd_blocks(void) { return sk_num_sms() * 2; }
+extern "C" int sk_rmsnorm_bwd_blocks(void) { return sk_num_sms() * 4; }
 int sk_rmsnorm_bwd_launch(const bf16* dy, const bf16* x, const bf16* w, const float* rstd, const bf16* dres, bf16* dx,
                           bf16* dw, float* dw_partial, int M, int D, int accumulate_dw, cudaStream_t s) {
   SK_REQUIRE(D % 8 == 0 && D <= 1024, "rmsnorm: D must be a multiple of 8 and <= 1024 (D=%d)", D);
@@ -633,18 +648,18 @@ int sk_rmsnorm_bwd_launch(const bf16* dy, const bf16* x, const bf16* w, const fl
   const size_t smem = (size_t)WARPS_PER_BLOCK * D * sizeof(float);
   rmsnorm_bwd_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, s>>>(dy, x, w, rstd, dres, dx, dw_partial, M, D);
   SK_LAUNCH_CHECK();
-  colsum_reduce_kernel<<<(D + 255) / 256, 256, 0, s>>>(dw_partial, dw, blocks, D, accumulate_dw);
+  colsum_reduce_kernel<<<(D + 31) / 32, 256, 0, s>>>(dw_partial, dw, blocks, D, accumulate_dw);
   SK_LAUNCH_CHECK();
   return 0;
 }
-constexpr int COLSUM_SPLITS = 64;
+constexpr int COLSUM_SPLITS = 512;
 extern "C" int sk_colsum_splits(void) { return COLSUM_SPLITS; }
 int sk_colsum_launch(const bf16* x, bf16* out, float* partial, int M, int N, int ld, int accumulate, cudaStream_t s) {
   SK_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
   dim3 grid((N / 8 + 127) / 128, COLSUM_SPLITS);
   colsum_partial_kernel<<<grid, 128, 0, s>>>(x, partial, M, N, ld);
   SK_LAUNCH_CHECK();
-  colsum_reduce_kernel<<<(N + 255) / 256, 256, 0, s>>>(partial, out, COLSUM_SPLITS, N, accumulate);
+  colsum_reduce_kernel<<<(N + 31) / 32, 256, 0, s>>>(partial, out, COLSUM_SPLITS, N, accumulate);
   SK_LAUNCH_CHECK();
   return 0;
 }

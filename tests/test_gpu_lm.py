@@ -56,6 +56,8 @@ def test_lm_matches_reference_golden(golden_dir):
     assert abs(float(opt.stats[0]) - float(z["total_norm"])) < 0.01 * float(z["total_norm"])
     sd_p = m.state_dict_hf()
     for k in p:
+        if k.endswith("k_proj.bias"):
+            continue  # softmax is invariant to a key bias: its true gradient is 0, Adam turns rounding noise into +-lr
         ref = u16_to_bf16(z["new::" + k]).view_as(p[k])
         # the first AdamW step moves every weight by ~lr*sign(grad) = 1e-3, i.e. only ~8 bf16 ulps of a 0.02-sized
         # weight: compare the update direction and size, tolerant of sign flips on near-zero gradients
@@ -86,7 +88,7 @@ def test_lm_forward_backward_vs_oracle(B, T, layers):
     assert rel_err(logits, ref_logits) < 8e-3, rel_err(logits, ref_logits)
     sd_g = m.state_dict_hf(grads=True)
     errs = {k: rel_err(sd_g[k].cpu(), ref_grads[k]) for k in p}
-    bad = {k: v for k, v in errs.items() if v > 2e-2}
+    bad = {k: v for k, v in errs.items() if v > 2e-2 and not k.endswith("k_proj.bias")}  # d/d(k bias) == 0 exactly
     assert not bad, bad
     # gradient accumulation: a second identical micro-batch doubles the gradient
     m.forward_backward(ids, labels, num_items_in_batch=n_items, accumulate=True)
