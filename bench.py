@@ -167,8 +167,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.require_cuda()
 
+    from slamkit_b200.trainer import GradSync
     model = B200UnitLM(LMConfig(), device=str(dev), max_batch=PER_GPU_BATCH, max_seq=SEQ, seed=0)
     opt = B200AdamW(model, lr=1e-3, max_grad_norm=0.5)
+    sync = GradSync(model, overlap=os.environ.get("SK_NO_OVERLAP") is None)
     n_items = float(PER_GPU_BATCH * SEQ * world)      # HF num_items_in_batch gathered over ranks (HF:trainer.py:2136)
     NB = 4
     host = [synth_batch(rank, i).pin_memory() for i in range(NB)]
@@ -176,15 +178,13 @@ def main():
 
     def step_device(i):
         model.forward_backward(devb[i % NB], devb[i % NB], num_items_in_batch=n_items)
-        if world > 1:
-            dist.all_reduce(model.grads)              # SUM: every rank already divided by the global token count
+        sync.reduce()      # bucketed SUM all-reduce overlapped with backward; ranks already divided by the global count
         opt.step()
 
     def step_e2e(i):
         ids = host[i % NB].to(dev, non_blocking=True)  # labels = ids (causal LM): one H2D copy feeds both
         model.forward_backward(ids, ids, num_items_in_batch=n_items)
-        if world > 1:
-            dist.all_reduce(model.grads)
+        sync.reduce()
         opt.step()
         return float(model.stats[0].item())           # D2H read of the loss
 

@@ -141,6 +141,10 @@ int sk_lm_forward(SkLm* lm, const int64_t* ids, const int64_t* labels, const int
  * (HF:trainer.py:2092-2154 num_items_in_batch semantics), else mean over valid targets. */
 int sk_lm_forward_backward(SkLm* lm, const int64_t* ids, const int64_t* labels, const int32_t* pos_ids, int B, int T,
                            float num_items, float dloss, int accumulate, float* stats, void* stream);
+/* Data-parallel overlap hook: n = n_layers+1 caller-owned cudaEvent_t handles; during sk_lm_forward_backward event l is
+ * recorded on the compute stream once layer l's gradients are final (event n_layers: final-norm part), so the host can
+ * enqueue that bucket's NCCL all-reduce on a side stream while the backward pass continues.  NULL/0 disables. */
+int sk_lm_set_backward_events(SkLm* lm, void* const* events, int n);
 /* bf16 [B*T, sk_lm_logits_ld()] logits of the last forward (valid columns: vocab_size). */
 const void* sk_lm_logits(const SkLm* lm);
 int sk_lm_logits_ld(const SkLm* lm);

@@ -431,7 +431,7 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __rest
 // heads and their query tiles.  Works on transposed score tiles S^T = K Q^T so P^T/dS^T are directly A operands.
 // ------------------------------------------------------------------------------------------------
 template <bool CAUSAL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 attn_bwd_dkdv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                      const bf16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta,
                      bf16* __restrict__ dk, bf16* __restrict__ dv, int T, int ld, int ldo, int ldg, int H, int group,
@@ -475,7 +475,6 @@ attn_bwd_dkdv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, con
   };
   if (n_iter > 0) issue(0, 0);
 
-  uint32_t ka[4][4], va[4][4];
   float dkacc[8][4], dvacc[8][4];
   zero_acc(dkacc);
   zero_acc(dvacc);
@@ -490,18 +489,18 @@ attn_bwd_dkdv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, con
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (it == 0) {
-      load_a_frags(sKV, warp * 16, ka);
-      load_a_frags(sKV + 8192, warp * 16, va);
-    }
     const int qt = qt_begin + it % per_head;
     const int q0 = qt * 64;
     const float* s_lse = sStat + (st * 2 + 0) * 64;
     const float* s_del = sStat + (st * 2 + 1) * 64;
 
+    // K / V A-fragments are re-read from their resident smem tiles each iteration (8 ldmatrix) instead of being
+    // pinned in 32 registers: that keeps the kernel under 170 registers -> 3 CTAs per SM
+    uint32_t fa[4][4];
+    load_a_frags(sKV, warp * 16, fa);
     float st_acc[8][4];  // S^T tile: rows = keys (this warp's 16), cols = 64 query rows
     zero_acc(st_acc);
-    gemm_a_bT(st_acc, ka, sQ + st * 8192);
+    gemm_a_bT(st_acc, fa, sQ + st * 8192);
     const bool need_mask = (CAUSAL && (q0 < k0 + 64)) || (q0 + 64 > T) || (k0 + 64 > T);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -523,7 +522,8 @@ attn_bwd_dkdv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, con
 
     float dp[8][4];
     zero_acc(dp);
-    gemm_a_bT(dp, va, sdO + st * 8192);  // dP^T = V dO^T
+    load_a_frags(sKV + 8192, warp * 16, fa);
+    gemm_a_bT(dp, fa, sdO + st * 8192);  // dP^T = V dO^T
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll

@@ -50,6 +50,9 @@ struct SkLm {
   float* d_chunk_partial = nullptr;
   int n_chunks = 0;
   int last_B = 0, last_T = 0;
+  // optional: events recorded on the compute stream as soon as a layer's gradients are final (index = layer; index
+  // n_layers = lm_head / final-norm part), so the host can start that bucket's all-reduce while backward continues
+  std::vector<cudaEvent_t> bwd_events;
 };
 
 namespace {
@@ -218,6 +221,7 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
   SK_TRY(linear_wgrad(M, lm->Vp, d, dlogits, hf, G + lm->off_head, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
   SK_TRY(sk_rmsnorm_bwd_launch(dh, wsp<bf16>(lm, w.X + w.sX * L), P + lm->off_final_norm, wsp<float>(lm, w.rstdf),
                                nullptr, dxA, G + lm->off_final_norm, dwp, M, d, accumulate, s));
+  if (!lm->bwd_events.empty()) SK_CUDA_CHECK(cudaEventRecord(lm->bwd_events[L], s));
   for (int l = L - 1; l >= 0; --l) {
     const LayerOff& o = lm->lo[l];
     bf16* x = wsp<bf16>(lm, w.X + w.sX * l);
@@ -251,6 +255,7 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
     SK_TRY(linear_dgrad(M, Q, d, dqkv, P + o.wqkv, dh, s));
     SK_TRY(linear_wgrad(M, Q, d, dqkv, h1, G + o.wqkv, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
     SK_TRY(sk_rmsnorm_bwd_launch(dh, x, P + o.ln1, r1, dxB, dxA, G + o.ln1, dwp, M, d, accumulate, s));
+    if (!lm->bwd_events.empty()) SK_CUDA_CHECK(cudaEventRecord(lm->bwd_events[l], s));
   }
   // embedding: tied -> add on top of the lm_head gradient just written; untied -> honour `accumulate`
   SK_TRY(sk_embed_bwd_launch(ids, dxA, wsp<float>(lm, w.embed_scratch), G + lm->off_embed, M, d, lm->V, lm->Vp,
@@ -385,6 +390,18 @@ int sk_lm_forward_backward(SkLm* lm, const int64_t* ids, const int64_t* labels, 
   SK_TRY(check_bound(lm, B, T, w));
   SK_TRY(forward_impl(lm, ids, labels, pos_ids, B, T, num_items, dloss, true, stats, w, (cudaStream_t)stream));
   return backward_impl(lm, ids, pos_ids, B, T, accumulate, w, (cudaStream_t)stream);
+}
+
+int sk_lm_set_backward_events(SkLm* lm, void* const* events, int n) {
+  SK_REQUIRE(lm, "sk_lm_set_backward_events: null handle");
+  if (events == nullptr || n == 0) {
+    lm->bwd_events.clear();
+    return 0;
+  }
+  SK_REQUIRE(n == lm->L + 1, "sk_lm_set_backward_events: expected n_layers+1 = %d events, got %d", lm->L + 1, n);
+  lm->bwd_events.assign(n, nullptr);
+  for (int i = 0; i < n; ++i) lm->bwd_events[i] = (cudaEvent_t)events[i];
+  return 0;
 }
 
 const void* sk_lm_logits(const SkLm* lm) {
