@@ -133,6 +133,108 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+HUBERT_B, HUBERT_S = 64, 480000                      # BASELINE.json configs[2]: batch 64 x 30 s @ 16 kHz
+HUBERT_FLOP_PER_CLIP = 292.10e9                        # SURVEY.md §8d (11 layers, T=750)
+HUBERT_T0 = 96015
+
+
+def synth_wav(rank: int, idx: int, B: int = HUBERT_B, S: int = HUBERT_S) -> torch.Tensor:
+    """0.1*randn clamped to +-1."""
+    g = torch.Generator().manual_seed(4321 + rank * 1_000_000 + idx)
+    return (0.1 * torch.randn(B, S, generator=g)).clamp_(-1, 1)
+
+
+def run_hubert_gpu(args, rank, local_rank, world, lib, dist):
+    """Secondary headline: HuBERT-25Hz unit extraction throughput (audio-hours/s), mHuBERT geometry, synthetic audio,
+    seeded random weights; every rank extracts its own batches (no collective on this path)."""
+    import ctypes as C
+    from slamkit_b200.feature_extractor import HubertB200Config, HubertB200FeatureExtractor, random_params
+    dev = torch.device("cuda", local_rank)
+    cfg = HubertB200Config()
+    fe = HubertB200FeatureExtractor(cfg, random_params(cfg, seed=0), device=str(dev), max_batch=HUBERT_B,
+                                    max_samples=HUBERT_S)
+    host = [synth_wav(rank, i).pin_memory() for i in range(2)]
+    devw = [h.to(dev) for h in host]
+    n = max(3, args.steps // 4)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def mx(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(2):
+        fe.units_device(devw[i % 2], None)
+    sync()
+    l0 = lib.sk_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        fe.units_device(devw[i % 2], None)
+    e1.record()
+    sync()
+    dev_ms = mx(e0.elapsed_time(e1))
+    launches = lib.sk_launch_count() - l0
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e2.record()
+    for i in range(n):
+        ids, nf = fe.units_device(host[i % 2], None)       # pinned host -> device inside
+        ids_h = ids.cpu()                                   # device -> host read of the labels (192 KB)
+    e3.record()
+    sync()
+    e2e_ms = mx(max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3))
+    hours = HUBERT_B * 30.0 / 3600.0 * world
+    out = {"metric": "HuBERT-25Hz unit extraction audio-hours/sec", "value": hours * n / (dev_ms / 1e3),
+           "unit": "audio-hours/s", "batches": n, "ms_per_batch": dev_ms / n,
+           "config": {"workload": "mHuBERT-25Hz geometry, 11 encoder layers + km500 argmin, batch 64 x 30 s @ 16 kHz "
+                                  "synthetic audio, split-bf16 (fp32-grade) tensor-core products", "parallelism": f"dp{world}"},
+           "e2e": {"value": hours * n / (e2e_ms / 1e3), "unit": "audio-hours/s",
+                   "h2d_bytes_per_step": HUBERT_B * HUBERT_S * 4, "d2h_bytes_per_step": int(ids_h.numel() * 4)},
+           "gpu_launches": int(launches), "dtype": "bf16x3 (split) / fp32 accumulate"}
+    if rank == 0:
+        pk = peaks()
+        lib.sk_prof_enable(1)
+        fe.units_device(devw[0], None)
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        lib.sk_prof_collect(ms, cnt)
+        lib.sk_prof_enable(0)
+        conv0_bytes = HUBERT_B * (HUBERT_T0 * 512 * 2 * 2 + (HUBERT_S + 80) * 4)
+        gbs = conv0_bytes / (ms[3] / 1e3) / 1e9 if ms[3] > 0 else None
+        out["roofline"] = {"bound": "hbm", "kernel": "conv0_apply_kernel (conv0 + GroupNorm + GELU, hi/lo channels-last)",
+                           "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": (gbs / pk["hbm_gbs"]) if gbs else None, "traffic": None,
+                           "algorithmic_bytes_per_launch": conv0_bytes, "peak_source": pk["source"],
+                           "breakdown_ms": {"gemm": ms[0], "attention": ms[1], "conv0_apply": ms[3],
+                                            "batch": dev_ms / n},
+                           "tensor_tflops_fp32_equivalent": HUBERT_FLOP_PER_CLIP * HUBERT_B / (dev_ms / n / 1e3) / 1e12}
+    del fe
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_hubert_reference(args):
+    """CPU arm of the secondary metric: the oracle (fp32 torch restatement of the reference's HF + sklearn path)."""
+    from oracle import hubert_oracle as HO
+    torch.set_num_threads(usable_cpus())
+    o = HO.OracleHubertConfig()
+    p = HO.init_hubert_params(o, seed=0)
+    wav = synth_wav(0, 0, 2, 160000)
+    HO.extract(p, o, wav[:1, :32000])
+    t0 = time.perf_counter()
+    HO.extract(p, o, wav)
+    dt = time.perf_counter() - t0
+    return {"value": 2 * 10.0 / 3600.0 / dt, "unit": "audio-hours/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "one batch of 2 x 10 s clips through the fp32 oracle (HF HuBERT restatement + k-means)"}
+
+
 def workload_config(world: int):
     return {"workload": "SLAM pretrain step: Qwen2.5-0.5B-shaped unit LM (358M, vocab 502), unit_hubert_25 tokens, "
                         "seq=1024, per-GPU micro-batch 8, clip 0.5 + AdamW, bf16 params/state",
@@ -147,12 +249,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-hubert", action="store_true", help="skip the secondary HuBERT audio-hours/s measurement")
+    ap.add_argument("--hubert-cpu", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.hubert_cpu:
+        print(json.dumps(run_hubert_reference(args)), flush=True)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -278,6 +385,19 @@ def main():
             cpu = {"value": None, "unit": "tokens/s", "cores": usable_cpus(), "kind": "port",
                    "sample": f"failed: {type(e).__name__}"}
 
+    hubert = None
+    if not args.skip_hubert:
+        del devb
+        hubert = run_hubert_gpu(args, rank, local_rank, world, lib, dist)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            import subprocess
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--hubert-cpu"], capture_output=True,
+                                   text=True, timeout=300)
+                hubert["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:
+                hubert["cpu_baseline"] = {"value": None, "sample": f"failed: {type(e).__name__}"}
+
     if rank == 0:
         line = {"metric": "speech-tokens/sec (SLAM seq=1024)", "value": value, "unit": "tokens/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -285,7 +405,8 @@ def main():
                 "config": workload_config(world), "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": PER_GPU_BATCH * SEQ * 8,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "final_loss": loss}
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "final_loss": loss,
+                "secondary": hubert}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

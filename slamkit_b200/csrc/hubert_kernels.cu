@@ -404,7 +404,9 @@ int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const 
     SK_CUDA_CHECK(cudaFuncSetAttribute(conv0_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
+  sk_prof_begin(3, s);
   conv0_apply_kernel<<<dim3(gx, B), 256, smem, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
+  sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;
 }

@@ -113,6 +113,37 @@ def from_hf_state_dict(sd: Dict[str, torch.Tensor], centers: np.ndarray, cfg: Hu
     return {k: v.detach().float() for k, v in p.items()}
 
 
+def random_params(cfg: HubertB200Config, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded random weights in the reference's parameter naming (synthetic benchmarks / smoke tests: no pretrained
+    mHuBERT checkpoint is reachable offline)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(shape, generator=g) * std
+
+    Cc, H, Fd, K, G = cfg.conv_dim, cfg.hidden, cfg.ffn, cfg.pos_conv_kernel, cfg.pos_conv_groups
+    p = {"conv0.weight": rn(Cc, 1, cfg.conv_kernel[0], std=math.sqrt(2.0 / cfg.conv_kernel[0])),
+         "gn.weight": 1.0 + 0.1 * rn(Cc), "gn.bias": 0.1 * rn(Cc)}
+    for i in range(1, len(cfg.conv_kernel)):
+        p[f"conv{i}.weight"] = rn(Cc, Cc, cfg.conv_kernel[i], std=math.sqrt(2.0 / (Cc * cfg.conv_kernel[i])))
+    p["fp.ln.weight"], p["fp.ln.bias"] = 1.0 + 0.1 * rn(Cc), 0.1 * rn(Cc)
+    p["fp.proj.weight"], p["fp.proj.bias"] = rn(H, Cc, std=1.0 / math.sqrt(Cc)), 0.02 * rn(H)
+    p["pos.v"] = rn(H, H // G, K, std=math.sqrt(4.0 / (K * H)))
+    p["pos.g"] = p["pos.v"].norm(dim=(0, 1), keepdim=True)
+    p["pos.bias"] = 0.02 * rn(H)
+    p["enc.ln.weight"], p["enc.ln.bias"] = 1.0 + 0.1 * rn(H), 0.1 * rn(H)
+    for l in range(cfg.layer):
+        q = f"layers.{l}."
+        for nm in ("q", "k", "v", "o"):
+            p[q + nm + ".weight"], p[q + nm + ".bias"] = rn(H, H, std=1.0 / math.sqrt(H)), 0.02 * rn(H)
+        p[q + "ln1.weight"], p[q + "ln1.bias"] = 1.0 + 0.1 * rn(H), 0.1 * rn(H)
+        p[q + "ff1.weight"], p[q + "ff1.bias"] = rn(Fd, H, std=1.0 / math.sqrt(H)), 0.02 * rn(Fd)
+        p[q + "ff2.weight"], p[q + "ff2.bias"] = rn(H, Fd, std=1.0 / math.sqrt(Fd)), 0.02 * rn(H)
+        p[q + "ln2.weight"], p[q + "ln2.bias"] = 1.0 + 0.1 * rn(H), 0.1 * rn(H)
+    p["kmeans.centers"] = rn(cfg.n_units, H)
+    return p
+
+
 class HubertB200FeatureExtractor(torch.nn.Module):
     """Drop-in for `HubertFeatureExtractor` (same constructor keys via `from_pretrained_args`, same `extract` contract)."""
 
