@@ -144,6 +144,11 @@ int sk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
                 int ldo, int causal, float scale, void* stream) {
   return sk_attn_fwd_launch(CBF(q), CBF(k), CBF(v), BF(o), lse, B, T, H, KVH, ld, ldo, causal, scale, S(stream));
 }
+int sk_attn_tc_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int KVH, int ld, int ldo, int causal,
+                   float scale, void* stream) {
+  SK_REQUIRE(qkv && o, "sk_attn_tc_fwd: null argument");
+  return sk_attn_tc_fwd_launch(CBF(qkv), BF(o), lse, B, T, H, KVH, ld, ldo, causal, scale, S(stream));
+}
 int sk_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                 float* delta, void* dq, void* dk, void* dv, int B, int T, int H, int KVH, int ld, int ldo, int ldg,
                 int causal, float scale, void* stream) {

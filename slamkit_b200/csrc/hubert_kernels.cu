@@ -137,38 +137,38 @@ __global__ void conv0_affine_kernel(const double* __restrict__ stats, const floa
   affine[(size_t)b * C + c] = make_float2((float)sc, (float)((double)beta[c] - m * sc));
 }
 
-// Pass 2: out[b, t, c] = GELU(conv(x)[c,t] * scale + shift), channels-last, hi/lo bf16.  One thread = one frame x 8
-// channels; a warp covers 256 consecutive channels of one frame -> 512 B coalesced stores per tensor.
-__global__ void __launch_bounds__(256)
+// Pass 2: out[b, t, c] = GELU(conv(x)[c,t] * scale + shift), channels-last, hi/lo bf16.  A thread owns 8 fixed
+// channels (its 8 x KW taps and 8 affine pairs live in registers for the whole kernel) and walks over frames; a warp
+// covers 256 consecutive channels of one frame -> 512-byte coalesced stores per tensor.  No shared memory.
+__global__ void __launch_bounds__(256, 2)
 conv0_apply_kernel(const float* __restrict__ wav, const float* __restrict__ w, const float2* __restrict__ affine,
                    bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int S, int pad, int T0, int C, int KW, int ST) {
-  extern __shared__ float s_w[];  // [C][KW] weights then [C] float2 affine
-  float2* s_aff = reinterpret_cast<float2*>(s_w + C * KW);
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < C * KW; i += blockDim.x) s_w[i] = w[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) s_aff[i] = affine[(size_t)b * C + i];
-  __syncthreads();
-  const float* wv = wav + (size_t)b * S;
-  const int groups = C / 8;                       // channel groups of 8
-  const int frames_per_block = blockDim.x / groups > 0 ? blockDim.x / groups : 1;
+  const int groups = C / 8;                       // channel groups of 8 (<= 256)
+  const int lanes_t = blockDim.x / groups;        // frames processed concurrently by a block (>= 1)
   const int cg = threadIdx.x % groups;
   const int tf = threadIdx.x / groups;
-  for (int t0 = blockIdx.x * frames_per_block; t0 < T0; t0 += gridDim.x * frames_per_block) {
-    const int t = t0 + tf;
-    if (tf >= frames_per_block || t >= T0) continue;
+  if (tf >= lanes_t) return;
+  float wr[8][KW_MAX];
+  float2 aff[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    aff[k] = affine[(size_t)b * C + cg * 8 + k];
+#pragma unroll
+    for (int j = 0; j < KW_MAX; ++j) wr[k][j] = j < KW ? __ldg(w + (cg * 8 + k) * KW + j) : 0.f;
+  }
+  const float* wv = wav + (size_t)b * S;
+  for (int t = blockIdx.x * lanes_t + tf; t < T0; t += gridDim.x * lanes_t) {
     float x[KW_MAX];
 #pragma unroll
     for (int j = 0; j < KW_MAX; ++j) x[j] = j < KW ? wav_at(wv, (long)ST * t + j, S, pad) : 0.f;
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = cg * 8 + k;
       float y = 0.f;
 #pragma unroll
-      for (int j = 0; j < KW_MAX; ++j)
-        if (j < KW) y = fmaf(s_w[c * KW + j], x[j], y);
-      const float2 a = s_aff[c];
-      v[k] = gelu_erf(fmaf(y, a.x, a.y));
+      for (int j = 0; j < KW_MAX; ++j) y = fmaf(wr[k][j], x[j], y);
+      v[k] = gelu_erf(fmaf(y, aff[k].x, aff[k].y));
     }
     uint4 hi, lo;
     split8(v, hi, lo);
@@ -396,16 +396,10 @@ int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const 
   SK_LAUNCH_CHECK();
   const int fpb = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
   int gx = (T0 + fpb - 1) / fpb;
-  const int cap = std::max(1, sk_num_sms() * 8 / B);
+  const int cap = std::max(1, sk_num_sms() * 4 / B);
   if (gx > cap) gx = cap;
-  const size_t smem = (size_t)C * KW * sizeof(float) + (size_t)C * sizeof(float2);
-  static bool attr = false;
-  if (!attr) {
-    SK_CUDA_CHECK(cudaFuncSetAttribute(conv0_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
-  }
   sk_prof_begin(3, s);
-  conv0_apply_kernel<<<dim3(gx, B), 256, smem, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
+  conv0_apply_kernel<<<dim3(gx, B), 256, 0, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;

@@ -71,6 +71,10 @@ int sk_attn_fwd_split_launch(const bf16* q_hi, const bf16* q_lo, const bf16* k_h
                              const bf16* v_lo, bf16* o_hi, bf16* o_lo, int B, int T, int H, int ld, int ldo, float scale,
                              cudaStream_t s);
 
+// attention_tc.cu (tcgen05 / TMEM flash attention)
+int sk_attn_tc_fwd_launch(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, int KVH, int ld, int ldo, int causal,
+                          float scale, cudaStream_t s);
+
 // hubert_kernels.cu
 int sk_split_f32_launch(const float* x, bf16* hi, bf16* lo, long n, cudaStream_t s);
 extern "C" int sk_conv0_nstat(void);

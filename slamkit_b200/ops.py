@@ -146,6 +146,16 @@ def attn_fwd(qkv: torch.Tensor, B: int, T: int, H: int, KVH: int, causal: bool, 
     return o, lse
 
 
+def attn_tc_fwd(qkv: torch.Tensor, B: int, T: int, H: int, KVH: int, causal: bool, scale: float):
+    """tcgen05 flash-attention forward (sk_attn_tc_fwd); same contract as attn_fwd."""
+    lib = L.require_cuda()
+    o = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
+    L.check(lib.sk_attn_tc_fwd(L.ptr(qkv), L.ptr(o), L.ptr(lse), B, T, H, KVH, qkv.stride(0), o.stride(0), int(causal),
+                               L.f32(scale), L.stream_ptr()))
+    return o, lse
+
+
 def attn_bwd(qkv, o, d_o, lse, B, T, H, KVH, causal: bool, scale: float) -> torch.Tensor:
     lib = L.require_cuda()
     hd = 64

@@ -236,6 +236,24 @@ def test_attention_fwd_bwd(B, T, H, KVH, causal):
     assert rel_err(dqkv[:, nk:], dqkv_ref[:, nk:]) < 1e-2, "dv"
 
 
+@pytest.mark.parametrize("B,T,H,KVH,causal", [(2, 256, 4, 2, True), (1, 1024, 14, 2, True), (2, 200, 2, 1, True),
+                                              (2, 750, 4, 4, False), (1, 77, 2, 2, False), (8, 1024, 14, 2, True)])
+def test_attention_tc_fwd(B, T, H, KVH, causal):
+    """tcgen05/TMEM forward against the fp32 reference (and therefore against the mma.sync kernel's contract)."""
+    from slamkit_b200 import ops
+    hd = 64
+    qkv = _randn(B * T, (H + 2 * KVH) * hd, seed=5)
+    scale = 1.0 / math.sqrt(hd)
+    o, lse = ops.attn_tc_fwd(qkv.to(DEV), B, T, H, KVH, causal, scale)
+    if B * H * T * T <= 2 * 14 * 1024 * 1024:
+        o_ref, lse_ref, _ = _attn_ref(qkv, B, T, H, KVH, causal, scale)
+    else:  # full LM shape: the (already validated) warp-level kernel is the reference
+        o2, lse2 = ops.attn_fwd(qkv.to(DEV), B, T, H, KVH, causal, scale)
+        o_ref, lse_ref = o2.cpu().float(), lse2.cpu()
+    assert rel_err(o.cpu(), o_ref) < 5e-3, rel_err(o.cpu(), o_ref)
+    assert max_abs(lse.cpu(), lse_ref) < 2e-3
+
+
 # ---------------------------------------------------------------------------------------------- optimiser
 def test_adamw_matches_oracle_and_torch():
     from slamkit_b200 import ops
