@@ -12,6 +12,7 @@
 // MMAs.  q/k/v are column slices of the fused projection [B*T, ld]; one tensor map serves all three.
 #include "kernels.h"
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -21,7 +22,7 @@ constexpr int AT_THREADS = 192;
 constexpr uint32_t SQ_BYTES = AT_BR * 128;        // 16 KB: [128 rows][64 dims] bf16
 constexpr uint32_t SKV_BYTES = AT_BC * 128;       // 16 KB each for K and V
 constexpr uint32_t SP_BYTES = 2 * AT_BR * 128;    // 32 KB: two 64-key K-blocks of [128 rows][64 keys]
-constexpr uint32_t AT_SMEM = SQ_BYTES + 2 * SKV_BYTES + SP_BYTES + 256 + 1024;   // 81.25 KB -> 2 CTAs / SM
+constexpr uint32_t AT_SMEM = SQ_BYTES + 3 * SKV_BYTES + SP_BYTES + 256 + 1024;   // 97.25 KB -> 2 CTAs / SM
 
 SK_DEVINL void tmem_ld_32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 SK_DEVINL void tmem_st_32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -44,12 +45,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
-  const uint32_t sK = sQ + SQ_BYTES;
-  const uint32_t sV = sK + SKV_BYTES;
+  const uint32_t sK = sQ + SQ_BYTES;           // two K stages
+  const uint32_t sV = sK + 2 * SKV_BYTES;
   const uint32_t sP = sV + SKV_BYTES;
   const uint32_t bar = sP + SP_BYTES;
-  const uint32_t q_full = bar, k_full = bar + 8, k_empty = bar + 16, v_full = bar + 24, v_empty = bar + 32,
-                 s_full = bar + 40, s_empty = bar + 48, p_full = bar + 56, o_done = bar + 64, tmem_slot = bar + 72;
+  const uint32_t q_full = bar, k_full = bar + 8 /*[2]*/, k_empty = bar + 24 /*[2]*/, v_full = bar + 40, v_empty = bar + 48,
+                 s_full = bar + 56, s_empty = bar + 64, p_full = bar + 72, o_done = bar + 80, tmem_slot = bar + 88;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,7 +66,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
     mbar_init(k_full, 1);
+    mbar_init(k_full + 8, 1);
     mbar_init(k_empty, 1);
+    mbar_init(k_empty + 8, 1);
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
@@ -89,30 +92,47 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       mbar_arrive_expect_tx(q_full, SQ_BYTES);
       tma_load_2d(sQ, &tmQKV, q_full, h * 64, row_base + q0);
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(k_empty, (j & 1) ^ 1u);
-        mbar_arrive_expect_tx(k_full, SKV_BYTES);
-        tma_load_2d(sK, &tmQKV, k_full, (H + g) * 64, row_base + j * AT_BC);
-        mbar_wait(v_empty, (j & 1) ^ 1u);
-        mbar_arrive_expect_tx(v_full, SKV_BYTES);
-        tma_load_2d(sV, &tmQKV, v_full, (H + KVH + g) * 64, row_base + j * AT_BC);
+        const int st = j & 1;
+        mbar_wait_sleep(k_empty + 8 * st, ((j >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(k_full + 8 * st, SKV_BYTES);
+        tma_load_2d(sK + st * SKV_BYTES, &tmQKV, k_full + 8 * st, (H + g) * 64, row_base + j * AT_BC);
+        if (j >= 1) {   // V_{j-1} is issued one step behind K_j so that K_0 and K_1 go out back to back
+          mbar_wait_sleep(v_empty, ((j - 1) & 1) ^ 1u);
+          mbar_arrive_expect_tx(v_full, SKV_BYTES);
+          tma_load_2d(sV, &tmQKV, v_full, (H + KVH + g) * 64, row_base + (j - 1) * AT_BC);
+        }
       }
+      mbar_wait_sleep(v_empty, ((n_kv - 1) & 1) ^ 1u);
+      mbar_arrive_expect_tx(v_full, SKV_BYTES);
+      tma_load_2d(sV, &tmQKV, v_full, (H + KVH + g) * 64, row_base + (n_kv - 1) * AT_BC);
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc(1u, 0u, 0u, 128, 128);   // S = Q K^T: A, B K-major
       constexpr uint32_t idesc_o = umma_idesc(1u, 0u, 1u, 128, 64);    // O += P V: A K-major, B (V) MN-major
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(k_full, j & 1);
-        mbar_wait(s_empty, (j & 1) ^ 1u);      // softmax finished reading the previous S
-        tc_fence_after();
+      auto issue_s = [&](int j) {
+        const uint32_t sKj = sK + (j & 1) * SKV_BYTES;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_f16(tS, umma_desc_sw128(sQ + k * 32, 16, 1024), umma_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k > 0);
+          tc_mma_f16(tS, umma_desc_sw128(sQ + k * 32, 16, 1024), umma_desc_sw128(sKj + k * 32, 16, 1024), idesc_s, k > 0);
         tc_commit(s_full);
-        tc_commit(k_empty);                    // K buffer free once the S MMAs retire
-        mbar_wait(p_full, j & 1);              // P in smem, O rescaled
-        mbar_wait(v_full, j & 1);
+        tc_commit(k_empty + 8 * (j & 1));      // K stage free once these MMAs retire
+      };
+      mbar_wait_sleep(q_full, 0);
+      mbar_wait_sleep(k_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {
+          // S_{j+1} is issued BEFORE P_j is needed: the softmax warps copied S_j to registers (s_empty), so the tensor
+          // pipe computes the next scores while they do exp / pack / correction for this tile
+          mbar_wait_sleep(k_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
+          mbar_wait_sleep(s_empty, j & 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait_sleep(p_full, j & 1);          // P_j in smem, O rescaled
+        mbar_wait_sleep(v_full, j & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -137,48 +157,42 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const bool need_mask = (CAUSAL && k0 + AT_BC - 1 > q0) || (k0 + AT_BC > T);
-      // pass 1: row max
-      float mx = m_run;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32(tS + lane_off + c * 32, v);
-        tmem_ld_wait();
+      // the whole 128-key row of S lives in registers: ONE pass over TMEM (all four loads in flight, one wait)
+      uint32_t v[4][32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (need_mask) {
+      for (int c = 0; c < 4; ++c) tmem_ld_32(tS + lane_off + c * 32, v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);       // S consumed: the next S MMA may overwrite it
+      if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
             const int key = k0 + c * 32 + i;
-            if (key >= T || (CAUSAL && key > qrow)) s = -INFINITY;
+            if (key >= T || (CAUSAL && key > qrow)) v[c][i] = 0xff800000u;  // -inf
           }
-          mx = fmaxf(mx, s);
-        }
       }
+      float mx = m_run;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c][i]));
       const float m_new = mx;
       const float mb = (m_new == -INFINITY) ? 0.f : m_new * sl2;
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * sl2 - mb);
-      // pass 2: p = exp2(s*c - m*c) -> bf16 -> swizzled smem (A operand of the PV MMA)
-      float rs = 0.f;
-#pragma unroll 1
+      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * sl2 - mb);
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32(tS + lane_off + c * 32, v);
-        tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
-          if (need_mask) {
-            const int key = k0 + c * 32 + 2 * i;
-            if (key >= T || (CAUSAL && key > qrow)) s0 = -INFINITY;
-            if (key + 1 >= T || (CAUSAL && key + 1 > qrow)) s1 = -INFINITY;
-          }
-          const float p0 = exp2f(s0 * sl2 - mb), p1 = exp2f(s1 * sl2 - mb);
-          // the row sum uses the bf16-rounded probabilities that the PV MMA will actually multiply
-          const uint32_t w = pack_bf16(p0, p1);
-          const float2 pr = unpack_bf16(w);
-          rs += pr.x + pr.y;
-          pk[i] = w;
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, -mb));
+          rs0 += p0;
+          rs1 += p1;
+          pk[i] = pack_bf16(p0, p1);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -189,9 +203,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
                        : "memory");
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);       // S fully consumed
+      const float rs = rs0 + rs1;
+
       l_run = l_run * alpha + rs;
       m_run = m_new;
       // correction: rescale O when this row's max moved (skipped warp-wide when no lane needs it)

@@ -121,6 +121,26 @@ SK_DEVINL uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+SK_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Single-thread role waits (TMA producer / MMA issuer): back off with nanosleep so the spinning lane does not steal
+// issue slots from the compute warps sharing its scheduler.  Still bounded (trap after ~4 s).
+SK_DEVINL void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if ((++spins & 0xfffu) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+      printf("slamkit_b200: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
 // Bounded wait: a mis-programmed pipeline traps after ~4 s instead of hanging the GPU box.
 SK_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

@@ -9,6 +9,7 @@
 #include <vector>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 constexpr int64_t ALIGN_ELEMS = 64;  // 128-byte alignment of every tensor in the flat buffers
@@ -50,6 +51,7 @@ struct SkLm {
   float* d_chunk_partial = nullptr;
   int n_chunks = 0;
   int last_B = 0, last_T = 0;
+  int attn_tc = 1;   // tcgen05/TMEM attention kernels (SK_ATTN_TC=0 selects the warp-level mma.sync kernels)
   // optional: events recorded on the compute stream as soon as a layer's gradients are final (index = layer; index
   // n_layers = lm_head / final-norm part), so the host can start that bucket's all-reduce while backward continues
   std::vector<cudaEvent_t> bwd_events;
@@ -177,8 +179,11 @@ int forward_impl(SkLm* lm, const int64_t* ids, const int64_t* labels, const int3
     SK_TRY(sk_rmsnorm_fwd_launch(x, P + o.ln1, h1, r1, M, d, lm->cfg.rms_eps, s));
     SK_TRY(linear_fwd(M, lm->qkv_dim, d, h1, P + o.wqkv, qkv, lm->cfg.qkv_bias ? P + o.bqkv : nullptr, nullptr, s));
     SK_TRY(sk_rope_launch(qkv, lm->rope_cos, lm->rope_sin, pos_ids, M, T, lm->qkv_dim, lm->H + lm->KVH, lm->hd, 0, s));
-    SK_TRY(sk_attn_fwd_launch(qkv, qkv + lm->H * lm->hd, qkv + (lm->H + lm->KVH) * lm->hd, ao, lse, B, T, lm->H, lm->KVH,
-                              lm->qkv_dim, d, 1, scale, s));
+    if (lm->attn_tc)
+      SK_TRY(sk_attn_tc_fwd_launch(qkv, ao, lse, B, T, lm->H, lm->KVH, lm->qkv_dim, d, 1, scale, s));
+    else
+      SK_TRY(sk_attn_fwd_launch(qkv, qkv + lm->H * lm->hd, qkv + (lm->H + lm->KVH) * lm->hd, ao, lse, B, T, lm->H,
+                                lm->KVH, lm->qkv_dim, d, 1, scale, s));
     SK_TRY(linear_fwd(M, d, d, ao, P + o.wo, xmid, nullptr, x, s));
     SK_TRY(sk_rmsnorm_fwd_launch(xmid, P + o.ln2, h2, r2, M, d, lm->cfg.rms_eps, s));
     SK_TRY(linear_fwd(M, 2 * F, d, h2, P + o.wgu, gu, nullptr, nullptr, s));
@@ -285,6 +290,7 @@ int sk_lm_create(const SkLmConfig* cfg, SkLm** out) {
   lm->V = cfg->vocab_size;
   lm->Vp = (cfg->vocab_size + 63) / 64 * 64;
   lm->qkv_dim = (lm->H + 2 * lm->KVH) * lm->hd;
+  if (const char* e = getenv("SK_ATTN_TC")) lm->attn_tc = atoi(e);
   lm->lo.resize(lm->L);
   for (int l = 0; l < lm->L; ++l) {
     const std::string p = "layers." + std::to_string(l) + ".";
