@@ -88,6 +88,11 @@ int sk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
  * qkv points at the fused [B*T, ld] projection: H q-heads, then KVH k-heads, then KVH v-heads, 64 columns each. */
 int sk_attn_tc_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int KVH, int ld, int ldo, int causal,
                    float scale, void* stream);
+/* tcgen05 backward: dqkv (same fused layout as qkv, pitch ldg) from d_o; delta fp32 [B,H,T] and partial fp32
+ * [B,H,T,128] are caller scratch.  Deterministic (per-head partials reduced over the GQA group in a fixed order). */
+int sk_attn_tc_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, float* partial,
+                   void* dqkv, int B, int T, int H, int KVH, int ld, int ldo, int ldg, int causal, float scale,
+                   void* stream);
 int sk_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                 float* delta, void* dq, void* dk, void* dv, int B, int T, int H, int KVH, int ld, int ldo, int ldg,
                 int causal, float scale, void* stream);

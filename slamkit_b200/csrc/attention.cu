@@ -734,3 +734,12 @@ int sk_attn_fwd_split_launch(const bf16* q_hi, const bf16* q_lo, const bf16* k_h
   SK_LAUNCH_CHECK();
   return 0;
 }
+
+int sk_attn_delta_launch(const bf16* o, const bf16* d_o, float* delta, int B, int T, int H, int ldo, cudaStream_t s) {
+  const long total = (long)B * T * H * 8;
+  sk_prof_begin(1, s);
+  attn_delta_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(o, d_o, delta, B, T, H, ldo);
+  sk_prof_end(s);
+  SK_LAUNCH_CHECK();
+  return 0;
+}

@@ -13,6 +13,7 @@
 #include "kernels.h"
 #include <cudaTypedefs.h>
 #include <stdlib.h>
+#define SK_TRY_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 namespace {
 
@@ -182,6 +183,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       const float m_new = mx;
       const float mb = (m_new == -INFINITY) ? 0.f : m_new * sl2;
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * sl2 - mb);
+      // the P buffer (and O) are still being read by the previous PV MMA until o_done: wait before overwriting P
+      if (j > 0) {
+        mbar_wait(o_done, (j - 1) & 1);
+        tc_fence_after();
+      }
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -209,8 +215,6 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       m_run = m_new;
       // correction: rescale O when this row's max moved (skipped warp-wide when no lane needs it)
       if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1);          // previous PV MMA retired
-        tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
@@ -282,6 +286,489 @@ int sk_attn_tc_fwd_launch(const bf16* qkv, bf16* o, float* lse, int B, int T, in
   sk_prof_begin(1, s);
   if (causal) attn_tc_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, s>>>(tm, o, lse, T, ldo, H, KVH, scale);
   else attn_tc_fwd_kernel<false><<<grid, AT_THREADS, AT_SMEM, s>>>(tm, o, lse, T, ldo, H, KVH, scale);
+  sk_prof_end(s);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// Backward on tcgen05.  Two deterministic kernels like the warp-level version (no atomics):
+//   dQ    : CTA = (128-query tile, head, batch), loops over 64-key tiles; S and dP accumulate in TMEM, the thread that
+//           owns a query row turns them into dS (bf16, swizzled smem), dQ += dS K on the tensor pipe.
+//   dK/dV : CTA = (128-key tile, query head, batch), loops over 64-query tiles on transposed scores S^T = K Q^T and
+//           dP^T = V dO^T (thread == key row); P^T and dS^T go to smem as A operands of dV += P^T dO, dK += dS^T Q.
+//           Per-head fp32 partials are reduced over the GQA group in a fixed order by attn_tc_group_reduce_kernel.
+// K / V / Q / dO tiles that act as the B operand of the second GEMMs are read MN-major straight from the row-major
+// activations (no transposes anywhere).
+// =================================================================================================
+namespace {
+
+constexpr int BQ_BC = 64;                                   // keys per step in the dQ kernel
+constexpr uint32_t T64_BYTES = 64 * 128;                    // [64 rows][64 dims] bf16 tile
+constexpr uint32_t DQ_SMEM = 2 * SQ_BYTES + 4 * T64_BYTES + SQ_BYTES + 256 + 1024;   // Q, dO, K[2], V[2], dS
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
+                      const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
+                      const float* __restrict__ delta, bf16* __restrict__ dq, int T, int ldg, int H, int KVH, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base, sdO = sQ + SQ_BYTES, sK = sdO + SQ_BYTES, sV = sK + 2 * T64_BYTES,
+                 sdS = sV + 2 * T64_BYTES, bar = sdS + SQ_BYTES;
+  const uint32_t q_full = bar, k_full = bar + 8, k_empty = bar + 24, v_full = bar + 40, v_empty = bar + 56,
+                 sdp_full = bar + 72, sdp_empty = bar + 80, ds_full = bar + 88, ds_empty = bar + 96, dq_done = bar + 104,
+                 tmem_slot = bar + 112;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_qt = (T + AT_BR - 1) / AT_BR;
+  const int qt = n_qt - 1 - (int)blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int g = h / (H / KVH);
+  const int q0 = qt * AT_BR;
+  const int row_base = b * T;
+  const int n_kv = CAUSAL ? (min(T - 1, q0 + AT_BR - 1) / BQ_BC + 1) : (T + BQ_BC - 1) / BQ_BC;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV128);
+    tma_prefetch_desc(&tmQKV64);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full + 8 * s, 1);
+      mbar_init(k_empty + 8 * s, 1);
+      mbar_init(v_full + 8 * s, 1);
+      mbar_init(v_empty + 8 * s, 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_empty, 4);
+    mbar_init(ds_full, 4);
+    mbar_init(ds_empty, 1);
+    mbar_init(dq_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdQ = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * SQ_BYTES);
+      tma_load_2d(sQ, &tmQKV128, q_full, h * 64, row_base + q0);
+      tma_load_2d(sdO, &tmDO, q_full, h * 64, row_base + q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t par = ((j >> 1) & 1) ^ 1u;
+        mbar_wait_sleep(k_empty + 8 * st, par);
+        mbar_arrive_expect_tx(k_full + 8 * st, T64_BYTES);
+        tma_load_2d(sK + st * T64_BYTES, &tmQKV64, k_full + 8 * st, (H + g) * 64, row_base + j * BQ_BC);
+        mbar_wait_sleep(v_empty + 8 * st, par);
+        mbar_arrive_expect_tx(v_full + 8 * st, T64_BYTES);
+        tma_load_2d(sV + st * T64_BYTES, &tmQKV64, v_full + 8 * st, (H + KVH + g) * 64, row_base + j * BQ_BC);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(1u, 0u, 0u, 128, 64);    // S = Q K^T, dP = dO V^T (N = 64 keys)
+      constexpr uint32_t idesc_q = umma_idesc(1u, 0u, 1u, 128, 64);    // dQ += dS K : B = K tile MN-major
+      auto issue_sdp = [&](int j) {
+        const uint32_t sKj = sK + (j & 1) * T64_BYTES, sVj = sV + (j & 1) * T64_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tS, umma_desc_sw128(sQ + k * 32, 16, 1024), umma_desc_sw128(sKj + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tdP, umma_desc_sw128(sdO + k * 32, 16, 1024), umma_desc_sw128(sVj + k * 32, 16, 1024), idesc_s, k > 0);
+        tc_commit(sdp_full);
+        tc_commit(v_empty + 8 * (j & 1));
+      };
+      mbar_wait_sleep(q_full, 0);
+      mbar_wait_sleep(k_full, 0);
+      mbar_wait_sleep(v_full, 0);
+      tc_fence_after();
+      issue_sdp(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {
+          const int st = (j + 1) & 1;
+          mbar_wait_sleep(k_full + 8 * st, ((j + 1) >> 1) & 1);
+          mbar_wait_sleep(v_full + 8 * st, ((j + 1) >> 1) & 1);
+          mbar_wait_sleep(sdp_empty, j & 1);
+          tc_fence_after();
+          issue_sdp(j + 1);
+        }
+        mbar_wait_sleep(ds_full, j & 1);
+        tc_fence_after();
+        const uint32_t sKj = sK + (j & 1) * T64_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tdQ, umma_desc_sw128(sdS + k * 32, 16, 1024), umma_desc_sw128(sKj + k * 2048, 8192, 1024), idesc_q,
+                     (j > 0 || k > 0) ? 1u : 0u);
+        tc_commit(k_empty + 8 * (j & 1));
+        tc_commit(ds_empty);
+        if (j == n_kv - 1) tc_commit(dq_done);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int qrow = q0 + r;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float sl2 = scale * 1.4426950408889634f;
+    const bool row_ok = qrow < T;
+    const size_t soff = ((size_t)b * H + h) * T + (row_ok ? qrow : 0);
+    const float lse2 = row_ok ? lse[soff] * 1.4426950408889634f : 0.f;
+    const float del = row_ok ? delta[soff] : 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int k0 = j * BQ_BC;
+      mbar_wait(sdp_full, j & 1);
+      tc_fence_after();
+      uint32_t sv[2][32], dv[2][32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32(tS + lane_off + c * 32, sv[c]);
+        tmem_ld_32(tdP + lane_off + c * 32, dv[c]);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_empty);
+      const bool need_mask = (CAUSAL && k0 + BQ_BC - 1 > q0) || (k0 + BQ_BC > T) || (q0 + AT_BR > T);
+      mbar_wait(ds_empty, (j & 1) ^ 1u);         // previous dQ MMA finished reading the dS buffer
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * i]), sl2, -lse2));
+          float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * i + 1]), sl2, -lse2));
+          if (need_mask) {
+            const int key = k0 + c * 32 + 2 * i;
+            if (!row_ok || key >= T || (CAUSAL && key > qrow)) p0 = 0.f;
+            if (!row_ok || key + 1 >= T || (CAUSAL && key + 1 > qrow)) p1 = 0.f;
+          }
+          const float d0 = p0 * (__uint_as_float(dv[c][2 * i]) - del) * scale;
+          const float d1 = p1 * (__uint_as_float(dv[c][2 * i + 1]) - del) * scale;
+          pk[i] = pack_bf16(d0, d1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int chunk = c * 4 + u;           // 8 chunks of 8 keys in the 64-key row
+          const uint32_t dst = sdS + r * 128 + ((chunk ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
+                       "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+                       : "memory");
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    mbar_wait(dq_done, 0);
+    tc_fence_after();
+    bf16* op = dq + ((size_t)(row_base + qrow)) * ldg + h * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32(tdQ + lane_off + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1]));
+          w.y = pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3]));
+          w.z = pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]));
+          w.w = pack_bf16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]));
+          stg128(op + c * 32 + u * 8, w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+
+constexpr int BK_BR = 64;                                   // query rows per step in the dK/dV kernel
+constexpr uint32_t DKDV_SMEM = 2 * SKV_BYTES + 4 * T64_BYTES + 2 * SKV_BYTES + 2 * 2 * 64 * 4 + 256 + 1024;
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
+                        const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
+                        const float* __restrict__ delta, float* __restrict__ partial /*[B][H][T][128]*/, int T, int H,
+                        int KVH, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = smem_base, sV = sK + SKV_BYTES, sQ = sV + SKV_BYTES /*[2]*/, sdO = sQ + 2 * T64_BYTES /*[2]*/,
+                 sPT = sdO + 2 * T64_BYTES, sdST = sPT + SKV_BYTES, sStat = sdST + SKV_BYTES, bar = sStat + 2 * 2 * 64 * 4;
+  const uint32_t kv_full = bar, q_full = bar + 8, q_empty = bar + 24, sdp_full = bar + 40, sdp_empty = bar + 48,
+                 pds_full = bar + 56, pds_empty = bar + 64, acc_done = bar + 72, tmem_slot = bar + 80;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* stat_ptr = reinterpret_cast<float*>(smem_raw + (sStat - smem_u32(smem_raw)));   // [stage][lse|delta][64]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x;                   // key tile 0 has the most query tiles under the causal mask
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int g = h / (H / KVH);
+  const int k0 = kt * AT_BC;
+  const int row_base = b * T;
+  const int n_qt = (T + BK_BR - 1) / BK_BR;
+  const int qt_begin = CAUSAL ? (k0 / BK_BR) : 0;
+  const int n_it = n_qt - qt_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV128);
+    tma_prefetch_desc(&tmQKV64);
+    tma_prefetch_desc(&tmDO64);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full + 8 * s, 1);
+      mbar_init(q_empty + 8 * s, 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_empty, 4);
+    mbar_init(pds_full, 4);
+    mbar_init(pds_empty, 1);
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tST = tmem_base, tdPT = tmem_base + 64, tdK = tmem_base + 128, tdV = tmem_base + 192;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * SKV_BYTES);
+      tma_load_2d(sK, &tmQKV128, kv_full, (H + g) * 64, row_base + k0);
+      tma_load_2d(sV, &tmQKV128, kv_full, (H + KVH + g) * 64, row_base + k0);
+      for (int i = 0; i < n_it; ++i) {
+        const int st = i & 1;
+        mbar_wait_sleep(q_empty + 8 * st, ((i >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(q_full + 8 * st, 2 * T64_BYTES);
+        tma_load_2d(sQ + st * T64_BYTES, &tmQKV64, q_full + 8 * st, h * 64, row_base + (qt_begin + i) * BK_BR);
+        tma_load_2d(sdO + st * T64_BYTES, &tmDO64, q_full + 8 * st, h * 64, row_base + (qt_begin + i) * BK_BR);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(1u, 0u, 0u, 128, 64);    // S^T = K Q^T, dP^T = V dO^T (N = 64 queries)
+      constexpr uint32_t idesc_a = umma_idesc(1u, 0u, 1u, 128, 64);    // dV += P^T dO, dK += dS^T Q (B MN-major)
+      auto issue_sdp = [&](int i) {
+        const uint32_t sQi = sQ + (i & 1) * T64_BYTES, sdOi = sdO + (i & 1) * T64_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tST, umma_desc_sw128(sK + k * 32, 16, 1024), umma_desc_sw128(sQi + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tdPT, umma_desc_sw128(sV + k * 32, 16, 1024), umma_desc_sw128(sdOi + k * 32, 16, 1024), idesc_s, k > 0);
+        tc_commit(sdp_full);
+      };
+      if (n_it > 0) {
+        mbar_wait_sleep(kv_full, 0);
+        mbar_wait_sleep(q_full, 0);
+        tc_fence_after();
+        issue_sdp(0);
+      }
+      for (int i = 0; i < n_it; ++i) {
+        if (i + 1 < n_it) {
+          mbar_wait_sleep(q_full + 8 * ((i + 1) & 1), ((i + 1) >> 1) & 1);
+          mbar_wait_sleep(sdp_empty, i & 1);
+          tc_fence_after();
+          issue_sdp(i + 1);
+        }
+        mbar_wait_sleep(pds_full, i & 1);
+        tc_fence_after();
+        const uint32_t sQi = sQ + (i & 1) * T64_BYTES, sdOi = sdO + (i & 1) * T64_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tdV, umma_desc_sw128(sPT + k * 32, 16, 1024), umma_desc_sw128(sdOi + k * 2048, 8192, 1024), idesc_a,
+                     (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tdK, umma_desc_sw128(sdST + k * 32, 16, 1024), umma_desc_sw128(sQi + k * 2048, 8192, 1024), idesc_a,
+                     (i > 0 || k > 0) ? 1u : 0u);
+        tc_commit(q_empty + 8 * (i & 1));
+        tc_commit(pds_empty);
+        if (i == n_it - 1) tc_commit(acc_done);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // key row inside the tile == TMEM lane
+    const int key = k0 + r;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float sl2 = scale * 1.4426950408889634f;
+    const int tid = threadIdx.x - 64;            // 0..127 among the softmax warps
+    for (int i = 0; i < n_it; ++i) {
+      const int q0 = (qt_begin + i) * BK_BR;
+      // stage the 64 lse / delta values of this query tile (per-COLUMN quantities here) in smem
+      float* st_lse = stat_ptr + (i & 1) * 128;
+      {
+        const int qq = q0 + (tid & 63);
+        const size_t off = ((size_t)b * H + h) * T + (qq < T ? qq : 0);
+        const float val = qq < T ? ((tid < 64) ? lse[off] * 1.4426950408889634f : delta[off]) : 0.f;
+        st_lse[tid] = val;                       // [0,64): lse * log2e, [64,128): delta
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after();
+      uint32_t sv[2][32], dv[2][32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32(tST + lane_off + c * 32, sv[c]);
+        tmem_ld_32(tdPT + lane_off + c * 32, dv[c]);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_empty);
+      const bool need_mask = (CAUSAL && q0 < k0 + AT_BC) || (q0 + BK_BR > T) || (k0 + AT_BC > T);
+      mbar_wait(pds_empty, (i & 1) ^ 1u);        // previous dV / dK MMAs finished reading P^T / dS^T
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int qi = c * 32 + 2 * e;
+          const float2 l2 = *reinterpret_cast<const float2*>(st_lse + qi);
+          const float2 dl = *reinterpret_cast<const float2*>(st_lse + 64 + qi);
+          float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * e]), sl2, -l2.x));
+          float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * e + 1]), sl2, -l2.y));
+          if (need_mask) {
+            const int qrow = q0 + qi;
+            if (key >= T || qrow >= T || (CAUSAL && key > qrow)) p0 = 0.f;
+            if (key >= T || qrow + 1 >= T || (CAUSAL && key > qrow + 1)) p1 = 0.f;
+          }
+          pp[e] = pack_bf16(p0, p1);
+          pd[e] = pack_bf16(p0 * (__uint_as_float(dv[c][2 * e]) - dl.x) * scale,
+                            p1 * (__uint_as_float(dv[c][2 * e + 1]) - dl.y) * scale);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int chunk = c * 4 + u;
+          const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPT + off), "r"(pp[4 * u]), "r"(pp[4 * u + 1]),
+                       "r"(pp[4 * u + 2]), "r"(pp[4 * u + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdST + off), "r"(pd[4 * u]), "r"(pd[4 * u + 1]),
+                       "r"(pd[4 * u + 2]), "r"(pd[4 * u + 3]) : "memory");
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+    }
+    // epilogue: fp32 partial dK | dV rows of this (batch, head, key)
+    if (n_it > 0) {
+      mbar_wait(acc_done, 0);
+      tc_fence_after();
+    }
+    float* pp = partial + (((size_t)b * H + h) * T + key) * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {               // columns 0..63 = dK (TMEM 128..191), 64..127 = dV (192..255)
+      uint32_t v[32];
+      if (n_it > 0) {
+        tmem_ld_32(tdK + lane_off + c * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = 0u;
+      }
+      if (key < T) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<float4*>(pp + c * 32 + u * 4) = make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]),
+                                                                      __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// dk / dv (bf16, column slices of the fused gradient buffer) = sum over the GQA group's query heads, fixed order
+__global__ void attn_tc_group_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ dk, bf16* __restrict__ dv,
+                                            int B, int T, int H, int KVH, int ldg) {
+  const int group = H / KVH;
+  const long total = (long)B * KVH * T * 16;      // 16 threads per (b, g, t): 8 columns each of the 128 (dK | dV)
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i & 15);
+    const long rt = i >> 4;
+    const int t = (int)(rt % T);
+    const int gg = (int)((rt / T) % KVH);
+    const int b = (int)(rt / ((long)T * KVH));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < group; ++j) {
+      const float* src = partial + (((size_t)b * H + gg * group + j) * T + t) * 128 + c8 * 8;
+      const float4 a = *reinterpret_cast<const float4*>(src), c = *reinterpret_cast<const float4*>(src + 4);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += c.z; acc[7] += c.w;
+    }
+    bf16* dst = (c8 < 8 ? dk : dv) + ((size_t)b * T + t) * ldg + gg * 64 + (c8 & 7) * 8;
+    stg128(dst, make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                           pack_bf16(acc[6], acc[7])));
+  }
+}
+
+}  // namespace
+
+// Backward launcher.  qkv / dqkv share the fused [B*T, ld] layout; delta fp32 [B,H,T] and partial fp32 [B,H,T,128] are
+// caller-provided scratch (delta is filled here).
+int sk_attn_delta_launch(const bf16* o, const bf16* d_o, float* delta, int B, int T, int H, int ldo, cudaStream_t s);
+int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse, float* delta, float* partial,
+                          bf16* dqkv, int B, int T, int H, int KVH, int ld, int ldo, int ldg, int causal, float scale,
+                          cudaStream_t s) {
+  SK_REQUIRE(H % KVH == 0, "attention: H must be a multiple of KVH");
+  CUtensorMap tm128, tm64, tmdo128, tmdo64;
+  int rc;
+  if ((rc = sk_make_tmap_2d(&tm128, qkv, 2, (uint64_t)(H + 2 * KVH) * 64, (uint64_t)B * T, (uint64_t)ld, 64, 128))) return rc;
+  if ((rc = sk_make_tmap_2d(&tm64, qkv, 2, (uint64_t)(H + 2 * KVH) * 64, (uint64_t)B * T, (uint64_t)ld, 64, 64))) return rc;
+  if ((rc = sk_make_tmap_2d(&tmdo128, d_o, 2, (uint64_t)H * 64, (uint64_t)B * T, (uint64_t)ldo, 64, 128))) return rc;
+  if ((rc = sk_make_tmap_2d(&tmdo64, d_o, 2, (uint64_t)H * 64, (uint64_t)B * T, (uint64_t)ldo, 64, 64))) return rc;
+  static bool init = false;
+  if (!init) {
+    SK_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    SK_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    SK_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_dkdv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKDV_SMEM));
+    SK_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_dkdv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKDV_SMEM));
+    init = true;
+  }
+  SK_TRY_RC(sk_attn_delta_launch(o, d_o, delta, B, T, H, ldo, s));
+  sk_prof_begin(1, s);
+  dim3 g1((T + AT_BC - 1) / AT_BC, H, B), g2((T + AT_BR - 1) / AT_BR, H, B);
+  bf16* dq = dqkv;
+  bf16* dk = dqkv + H * 64;
+  bf16* dv = dqkv + (H + KVH) * 64;
+  if (causal) {
+    attn_tc_bwd_dkdv_kernel<true><<<g1, AT_THREADS, DKDV_SMEM, s>>>(tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale);
+    attn_tc_bwd_dq_kernel<true><<<g2, AT_THREADS, DQ_SMEM, s>>>(tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale);
+  } else {
+    attn_tc_bwd_dkdv_kernel<false><<<g1, AT_THREADS, DKDV_SMEM, s>>>(tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale);
+    attn_tc_bwd_dq_kernel<false><<<g2, AT_THREADS, DQ_SMEM, s>>>(tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale);
+  }
+  const long total = (long)B * KVH * T * 16;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > sk_num_sms() * 8) blocks = sk_num_sms() * 8;
+  attn_tc_group_reduce_kernel<<<blocks, 256, 0, s>>>(partial, dk, dv, B, T, H, KVH, ldg);
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;

@@ -28,7 +28,7 @@ struct WsLayout {
   int64_t X, h1, rstd1, qkv, ao, lse, xmid, h2, rstd2, gu, act;  // per-layer strides below
   int64_t sX, sh, srstd, sqkv, slse, sgu, sact;
   int64_t hf, rstdf, logits, dlogits, dxA, dxB, dh, dao, dqkv, dact, dgu, delta;
-  int64_t dw_partial, colsum_partial, ce_partial, embed_scratch, splitk, splitk_bytes, total;
+  int64_t dw_partial, colsum_partial, ce_partial, embed_scratch, splitk, splitk_bytes, attn_partial, total;
 };
 }  // namespace
 
@@ -51,7 +51,7 @@ struct SkLm {
   float* d_chunk_partial = nullptr;
   int n_chunks = 0;
   int last_B = 0, last_T = 0;
-  int attn_tc = 1;   // tcgen05/TMEM attention kernels (SK_ATTN_TC=0 selects the warp-level mma.sync kernels)
+  int attn_tc = 1;   // 0: warp-level mma.sync attention; 1: tcgen05 forward; 2: tcgen05 forward + backward (SK_ATTN_TC)
   // optional: events recorded on the compute stream as soon as a layer's gradients are final (index = layer; index
   // n_layers = lm_head / final-norm part), so the host can start that bucket's all-reduce while backward continues
   std::vector<cudaEvent_t> bwd_events;
@@ -114,6 +114,7 @@ WsLayout make_layout(const SkLm* lm, int B, int T) {
   w.embed_scratch = take((int64_t)lm->Vp * lm->d * 4);
   w.splitk_bytes = (int64_t)8 * lm->qkv_dim * lm->d * 4;   // up to 8 fp32 slabs of the largest split-K wgrad
   w.splitk = take(w.splitk_bytes);
+  w.attn_partial = take((int64_t)B * lm->H * T * 128 * 4);   // per-head fp32 dK|dV partials (tcgen05 backward)
   w.total = cur;
   return w;
 }
@@ -251,9 +252,13 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
     // attention
     SK_TRY(linear_dgrad(M, d, d, dxB, P + o.wo, dao, s));
     SK_TRY(linear_wgrad(M, d, d, dxB, ao, G + o.wo, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
-    SK_TRY(sk_attn_bwd_launch(qkv, qkv + lm->H * lm->hd, qkv + (lm->H + lm->KVH) * lm->hd, ao, dao, lse,
-                              wsp<float>(lm, w.delta), dqkv, dqkv + lm->H * lm->hd, dqkv + (lm->H + lm->KVH) * lm->hd, B,
-                              T, lm->H, lm->KVH, Q, d, Q, 1, scale, s));
+    if (lm->attn_tc >= 2)
+      SK_TRY(sk_attn_tc_bwd_launch(qkv, ao, dao, lse, wsp<float>(lm, w.delta), wsp<float>(lm, w.attn_partial), dqkv, B, T,
+                                   lm->H, lm->KVH, Q, d, Q, 1, scale, s));
+    else
+      SK_TRY(sk_attn_bwd_launch(qkv, qkv + lm->H * lm->hd, qkv + (lm->H + lm->KVH) * lm->hd, ao, dao, lse,
+                                wsp<float>(lm, w.delta), dqkv, dqkv + lm->H * lm->hd, dqkv + (lm->H + lm->KVH) * lm->hd,
+                                B, T, lm->H, lm->KVH, Q, d, Q, 1, scale, s));
     SK_TRY(sk_rope_launch(dqkv, lm->rope_cos, lm->rope_sin, pos_ids, M, T, Q, lm->H + lm->KVH, lm->hd, 1, s));
     if (lm->cfg.qkv_bias)
       SK_TRY(sk_colsum_launch(dqkv, G + o.bqkv, wsp<float>(lm, w.colsum_partial), M, Q, Q, accumulate, s));

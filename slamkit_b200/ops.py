@@ -156,6 +156,18 @@ def attn_tc_fwd(qkv: torch.Tensor, B: int, T: int, H: int, KVH: int, causal: boo
     return o, lse
 
 
+def attn_tc_bwd(qkv, o, d_o, lse, B, T, H, KVH, causal: bool, scale: float) -> torch.Tensor:
+    """tcgen05 flash-attention backward (sk_attn_tc_bwd); same contract as attn_bwd."""
+    lib = L.require_cuda()
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    partial = torch.empty((B, H, T, 128), device=qkv.device, dtype=torch.float32)
+    L.check(lib.sk_attn_tc_bwd(L.ptr(qkv), L.ptr(o), L.ptr(d_o), L.ptr(lse), L.ptr(delta), L.ptr(partial), L.ptr(dqkv),
+                               B, T, H, KVH, qkv.stride(0), o.stride(0), dqkv.stride(0), int(causal), L.f32(scale),
+                               L.stream_ptr()))
+    return dqkv
+
+
 def attn_bwd(qkv, o, d_o, lse, B, T, H, KVH, causal: bool, scale: float) -> torch.Tensor:
     lib = L.require_cuda()
     hd = 64

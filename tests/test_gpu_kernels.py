@@ -254,6 +254,26 @@ def test_attention_tc_fwd(B, T, H, KVH, causal):
     assert max_abs(lse.cpu(), lse_ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,T,H,KVH,causal", [(2, 256, 4, 2, True), (1, 1024, 14, 2, True), (2, 200, 2, 1, True),
+                                              (2, 750, 4, 4, False), (1, 77, 2, 2, False)])
+def test_attention_tc_bwd(B, T, H, KVH, causal):
+    from slamkit_b200 import ops
+    hd = 64
+    qkv = _randn(B * T, (H + 2 * KVH) * hd, seed=7)
+    d_o = _randn(B * T, H * hd, seed=8)
+    scale = 1.0 / math.sqrt(hd)
+    _, _, dqkv_ref = _attn_ref(qkv, B, T, H, KVH, causal, scale, d_o)
+    o, lse = ops.attn_tc_fwd(qkv.to(DEV), B, T, H, KVH, causal, scale)
+    dqkv = ops.attn_tc_bwd(qkv.to(DEV), o, d_o.to(DEV), lse, B, T, H, KVH, causal, scale)
+    dqkv2 = ops.attn_tc_bwd(qkv.to(DEV), o, d_o.to(DEV), lse, B, T, H, KVH, causal, scale)
+    assert torch.equal(dqkv, dqkv2)   # deterministic
+    dqkv = dqkv.cpu()
+    nq, nk = H * hd, (H + KVH) * hd
+    assert rel_err(dqkv[:, :nq], dqkv_ref[:, :nq]) < 1e-2, ("dq", rel_err(dqkv[:, :nq], dqkv_ref[:, :nq]))
+    assert rel_err(dqkv[:, nq:nk], dqkv_ref[:, nq:nk]) < 1e-2, ("dk", rel_err(dqkv[:, nq:nk], dqkv_ref[:, nq:nk]))
+    assert rel_err(dqkv[:, nk:], dqkv_ref[:, nk:]) < 1e-2, ("dv", rel_err(dqkv[:, nk:], dqkv_ref[:, nk:]))
+
+
 # ---------------------------------------------------------------------------------------------- optimiser
 def test_adamw_matches_oracle_and_torch():
     from slamkit_b200 import ops
