@@ -51,7 +51,7 @@ struct SkLm {
   float* d_chunk_partial = nullptr;
   int n_chunks = 0;
   int last_B = 0, last_T = 0;
-  int attn_tc = 1;   // 0: warp-level mma.sync attention; 1: tcgen05 forward; 2: tcgen05 forward + backward (SK_ATTN_TC)
+  int attn_tc = 2;   // 0: warp-level mma.sync attention; 1: tcgen05 forward; 2: tcgen05 forward + backward (SK_ATTN_TC)
   // optional: events recorded on the compute stream as soon as a layer's gradients are final (index = layer; index
   // n_layers = lm_head / final-norm part), so the host can start that bucket's all-reduce while backward continues
   std::vector<cudaEvent_t> bwd_events;
