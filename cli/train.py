@@ -139,7 +139,7 @@ def main(argv=None):
         ev.append(float(model.forward(b["input_ids"], labels=b["labels"]).loss))
     if rank == 0:
         os.makedirs(ta.output_dir, exist_ok=True)
-        torch.save({k: v.cpu() for k, v in model.state_dict_hf().items()}, os.path.join(ta.output_dir, "unit_lm_state_dict.pt"))
+        model.save_pretrained(ta.output_dir, base_model_name=cfg.model.config_args.base_model_name)   # HF UnitLM layout
         tok.save_pretrained(ta.output_dir)
         json.dump({"log": log, "eval_loss": sum(ev) / max(1, len(ev)), "steps": step}, open(os.path.join(ta.output_dir, "trainer_state.json"), "w"))
         print(json.dumps({"eval_loss": sum(ev) / max(1, len(ev)), "steps": step}), flush=True)

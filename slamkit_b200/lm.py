@@ -192,10 +192,49 @@ class B200UnitLM:
             out["lm.lm_head.weight"] = out["lm.model.embed_tokens.weight"]
         return out
 
+    # ---- checkpoints (HF layout) ------------------------------------------------------------
+    def save_pretrained(self, save_directory: str, base_model_name: str = "Qwen/Qwen2.5-0.5B") -> None:
+        """Writes `model.safetensors` with the `lm.`-prefixed names of `UnitLM.state_dict()` (base_model_prefix = "lm",
+        slamkit/model/unit_lm.py:87) and a `config.json` in the `UnitLMConfig` layout (unit_lm.py:32-79), so that
+        `UnitLM.from_pretrained(dir)` / cli/eval.py of the reference can consume a B200-trained model."""
+        import json
+        import os
+        from safetensors.torch import save_file
+        os.makedirs(save_directory, exist_ok=True)
+        sd = {k: v.contiguous().cpu() for k, v in self.state_dict_hf().items() if k != "lm.lm_head.weight" or not self.config.tie_embeddings}
+        save_file(sd, os.path.join(save_directory, "model.safetensors"), metadata={"format": "pt"})
+        c = self.config
+        base = {"model_type": "qwen2", "architectures": ["Qwen2ForCausalLM"], "hidden_size": c.hidden,
+                "intermediate_size": c.ffn, "num_hidden_layers": c.n_layers, "num_attention_heads": c.n_heads,
+                "num_key_value_heads": c.n_kv_heads, "vocab_size": c.vocab_size, "rms_norm_eps": c.rms_eps,
+                "max_position_embeddings": c.max_positions, "tie_word_embeddings": c.tie_embeddings, "hidden_act": "silu",
+                "rope_parameters": {"rope_theta": c.rope_theta, "rope_type": "default"}, "rope_theta": c.rope_theta,
+                "pad_token_id": c.pad_token_id, "bos_token_id": 1, "eos_token_id": 1, "torch_dtype": "bfloat16"}
+        cfg = {"model_type": "speech_language_model", "architectures": ["UnitLM"], "base_model_name": base_model_name,
+               "base_config": base, "vocab_size": c.vocab_size, "twist_init": False, "use_cache": False,
+               "tie_word_embeddings": c.tie_embeddings, "torch_dtype": "bfloat16",
+               "max_position_embeddings": c.max_positions}
+        json.dump(cfg, open(os.path.join(save_directory, "config.json"), "w"), indent=2)
+
+    @classmethod
+    def from_pretrained(cls, directory: str, device: str = "cuda:0", max_batch: int = 8, max_seq: int = 1024,
+                        trainable: bool = True) -> "B200UnitLM":
+        import json
+        import os
+        from safetensors.torch import load_file
+        cfg = json.load(open(os.path.join(directory, "config.json")))
+        b = cfg["base_config"]
+        theta = (b.get("rope_parameters") or {}).get("rope_theta", b.get("rope_theta", 10000.0))
+        lm_cfg = LMConfig(vocab_size=cfg["vocab_size"], hidden=b["hidden_size"], n_layers=b["num_hidden_layers"],
+                          n_heads=b["num_attention_heads"], n_kv_heads=b["num_key_value_heads"],
+                          head_dim=b["hidden_size"] // b["num_attention_heads"], ffn=b["intermediate_size"],
+                          max_positions=max(max_seq, 2048), rms_eps=b["rms_norm_eps"], rope_theta=float(theta),
+                          tie_embeddings=bool(b.get("tie_word_embeddings", True)), pad_token_id=b.get("pad_token_id", 0))
+        m = cls(lm_cfg, device=device, max_batch=max_batch, max_seq=max_seq, trainable=trainable)
+        m.load_hf_state_dict(load_file(os.path.join(directory, "model.safetensors")))
+        return m
+
     # ---- compute -----------------------------------------------------------------------------------------------
-    @staticmethod
-    def _labels_with_mask(input_ids, labels, attention_mask):
-        return labels
 
     def _prep(self, input_ids: torch.Tensor, position_ids: Optional[torch.Tensor]):
         assert input_ids.dim() == 2 and input_ids.dtype == torch.int64

@@ -28,7 +28,7 @@ def test_extract_prepare_train_pipeline(tmp_path):
     for r in recs:
         assert len(r["units"]) == len(r["duration"]) > 0 and all(0 <= u < 500 for u in r["units"])
         assert all(a != b for a, b in zip(r["units"], r["units"][1:]))      # deduplicated
-    assert sum(recs[0]["duration"]) == 150                                    # 48000 samples -> 150 frames at 25 Hz
+    assert sum(recs[0]["duration"]) == 75                                     # 48000 samples = 3 s -> 75 frames at 25 Hz
     out_dir = str(tmp_path / "tokens")
     tok_file = prepare_tokens.main([f"data_path={feats}", f"out_path={out_dir}"])
     lines = [json.loads(l) for l in open(tok_file)]
@@ -41,7 +41,7 @@ def test_extract_prepare_train_pipeline(tmp_path):
                       "+training_args.logging_steps=1", "training_args.warmup_steps=2", "training_args.warmup_ratio=0",
                       f"training_args.output_dir={tmp_path}/run"])
     assert len(log) == 12 and log[-1]["loss"] < log[0]["loss"]
-    assert os.path.exists(tmp_path / "run" / "unit_lm_state_dict.pt")
+    assert os.path.exists(tmp_path / "run" / "model.safetensors") and os.path.exists(tmp_path / "run" / "config.json")
     st = json.load(open(tmp_path / "run" / "trainer_state.json"))
     assert st["steps"] == 12 and st["eval_loss"] > 0
     assert json.load(open(tmp_path / "run" / "tokeniser_config.json"))["num_units"] == 500

@@ -179,3 +179,25 @@ def test_grad_norm_and_clip_matches_torch():
     assert float(opt.stats[0]) == float(total), (float(opt.stats[0]), float(total))  # bf16-emulated total norm, exact
     exact = torch.sqrt(sum((v.float() ** 2).sum() for v in fake.values()))
     assert abs(float(opt.stats[2]) - float(exact)) < 1e-4 * float(exact)
+
+
+def test_hf_layout_checkpoint_roundtrip(tmp_path):
+    """save_pretrained writes the reference's UnitLM layout (lm.-prefixed safetensors + UnitLMConfig json): reloading
+    gives bit-identical logits, and the tensor names / shapes are exactly those of the oracle's HF-named parameters."""
+    import json
+    from safetensors.torch import load_file
+    from oracle import lm_oracle as O
+    from slamkit_b200.lm import B200UnitLM
+    cfg_o = O.OracleLMConfig(vocab_size=502, hidden=128, n_layers=2, n_heads=2, n_kv_heads=1, head_dim=64, ffn=256)
+    m, p = _mk(cfg_o, 3, 2, 64)
+    d = str(tmp_path / "ckpt")
+    m.save_pretrained(d)
+    sd = load_file(d + "/model.safetensors")
+    assert set(sd.keys()) == set(p.keys())
+    for k in p:
+        assert sd[k].shape == p[k].shape and torch.equal(sd[k], p[k]), k
+    c = json.load(open(d + "/config.json"))
+    assert c["model_type"] == "speech_language_model" and c["base_config"]["rope_parameters"]["rope_theta"] == 10000.0
+    m2 = B200UnitLM.from_pretrained(d, device=DEV, max_batch=2, max_seq=64)
+    ids = torch.randint(2, 502, (2, 64), generator=torch.Generator().manual_seed(0))
+    assert torch.equal(m.forward(ids).logits.clone(), m2.forward(ids).logits)
