@@ -154,6 +154,15 @@ int sk_lm_forward_backward(SkLm* lm, const int64_t* ids, const int64_t* labels, 
  * recorded on the compute stream once layer l's gradients are final (event n_layers: final-norm part), so the host can
  * enqueue that bucket's NCCL all-reduce on a side stream while the backward pass continues.  NULL/0 disables. */
 int sk_lm_set_backward_events(SkLm* lm, void* const* events, int n);
+/* Preference optimisation (DPO, cli/preference_alignment_train.py -> trl.DPOTrainer): the loss is not a
+ * plain CE, but its logit gradient is a per-SEQUENCE-weighted CE gradient.  sk_lm_forward_rows runs the forward pass
+ * and returns the per-position NLL (fp32 [B*T], 0 where the shifted label is -100) with all activations kept in the
+ * workspace; the host turns per-sequence sums into DPO weights; sk_lm_backward_weighted then back-propagates
+ * d loss / d logits[row] = row_weight[row] * (softmax - onehot) through the same activations. */
+int sk_lm_forward_rows(SkLm* lm, const int64_t* ids, const int64_t* labels, const int32_t* pos_ids, int B, int T,
+                       float* row_nll, float* stats, void* stream);
+int sk_lm_backward_weighted(SkLm* lm, const int64_t* ids, const int64_t* labels, const int32_t* pos_ids, int B, int T,
+                            const float* row_weight, int accumulate, float* stats, void* stream);
 /* bf16 [B*T, sk_lm_logits_ld()] logits of the last forward (valid columns: vocab_size). */
 const void* sk_lm_logits(const SkLm* lm);
 int sk_lm_logits_ld(const SkLm* lm);

@@ -53,7 +53,8 @@ int sk_swiglu_fwd_launch(const bf16* gu, bf16* act, int M, int F, cudaStream_t s
 int sk_swiglu_bwd_launch(const bf16* gu, const bf16* dact, bf16* dgu, int M, int F, cudaStream_t s);
 extern "C" int sk_ce_blocks(int M);
 int sk_ce_launch(const bf16* logits, const int64_t* labels, bf16* dlogits, float* partial, float* row_nll,
-                 float* stats_out, int M, int T, int V, int ldl, float num_items, float dloss, cudaStream_t s);
+                 float* stats_out, int M, int T, int V, int ldl, float num_items, float dloss, cudaStream_t s,
+                 const float* row_weight = nullptr);
 int sk_gradnorm_launch(const bf16* g, const long* chunk_start, const int* chunk_len, int n_chunks,
                        const int* tensor_chunk_begin, int n_tensors, float* partial, float max_norm, int emulate_bf16,
                        float* stats_out, cudaStream_t s);

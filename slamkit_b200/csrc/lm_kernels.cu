@@ -363,8 +363,8 @@ constexpr int CE_MAX_VEC = 2;  // up to 512 padded columns per row
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 ce_fwd_bwd_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ labels, bf16* __restrict__ dlogits,
-                  float* __restrict__ partial /*[grid][2]*/, float* __restrict__ row_nll /*[M] or null*/, int M, int T,
-                  int V, int ldl, float grad_scale) {
+                  float* __restrict__ partial /*[grid][2]*/, float* __restrict__ row_nll /*[M] or null*/,
+                  const float* __restrict__ row_weight /*[M] or null*/, int M, int T, int V, int ldl, float grad_scale) {
   __shared__ float s_loss[WARPS_PER_BLOCK], s_cnt[WARPS_PER_BLOCK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -416,6 +416,7 @@ ce_fwd_bwd_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ l
     if (row_nll && lane == 0) row_nll[row] = valid ? (lse - tgt_logit) : 0.f;
     if (dlogits) {
       const float inv = 1.0f / se;
+      const float gs = row_weight ? grad_scale * row_weight[row] : grad_scale;
 #pragma unroll
       for (int j = 0; j < CE_MAX_VEC; ++j) {
         const int c = (lane + 32 * j) * 8;
@@ -425,7 +426,7 @@ ce_fwd_bwd_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ l
           for (int k = 0; k < 8; ++k) {
             float pr = valid ? expf(v[j][k] - mx) * inv : 0.f;
             if (valid && c + k == (int)target) pr -= 1.f;
-            o[k] = pr * grad_scale;
+            o[k] = pr * gs;
           }
           stg128(dlogits + (size_t)row * ldl + c,
                  make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7])));
@@ -687,11 +688,12 @@ extern "C" int sk_ce_blocks(int M) { return (M + WARPS_PER_BLOCK - 1) / WARPS_PE
 // stats_out: float[3] = {loss, n_valid, nll_sum}.  num_items > 0: loss = sum/num_items (reference 'sum' path);
 // num_items <= 0: mean over valid tokens.  dloss scales the gradient.
 int sk_ce_launch(const bf16* logits, const int64_t* labels, bf16* dlogits, float* partial, float* row_nll,
-                 float* stats_out, int M, int T, int V, int ldl, float num_items, float dloss, cudaStream_t s) {
+                 float* stats_out, int M, int T, int V, int ldl, float num_items, float dloss, cudaStream_t s,
+                 const float* row_weight) {
   SK_REQUIRE(ldl % 8 == 0 && ldl <= CE_MAX_VEC * 256, "ce: padded vocab must be a multiple of 8 and <= %d", CE_MAX_VEC * 256);
   const int blocks = sk_ce_blocks(M);
   const float gs = num_items > 0.f ? dloss / num_items : dloss;
-  ce_fwd_bwd_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(logits, labels, dlogits, partial, row_nll, M, T, V, ldl, gs);
+  ce_fwd_bwd_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(logits, labels, dlogits, partial, row_nll, row_weight, M, T, V, ldl, gs);
   SK_LAUNCH_CHECK();
   ce_finalize_kernel<<<1, 256, 0, s>>>(partial, blocks, num_items, stats_out);
   SK_LAUNCH_CHECK();

@@ -156,7 +156,8 @@ int check_bound(const SkLm* lm, int B, int T, const WsLayout& w) {
 }
 
 int forward_impl(SkLm* lm, const int64_t* ids, const int64_t* labels, const int32_t* pos_ids, int B, int T,
-                 float num_items, float dloss, bool want_dlogits, float* stats, const WsLayout& w, cudaStream_t s) {
+                 float num_items, float dloss, bool want_dlogits, float* stats, const WsLayout& w, cudaStream_t s,
+                 float* row_nll = nullptr) {
   const int M = B * T, d = lm->d, F = lm->F, L = lm->L;
   const bf16* P = lm->params;
   bf16* X0 = wsp<bf16>(lm, w.X);
@@ -198,7 +199,7 @@ int forward_impl(SkLm* lm, const int64_t* ids, const int64_t* labels, const int3
   SK_TRY(linear_fwd(M, lm->Vp, d, hf, P + lm->off_head, logits, nullptr, nullptr, s));
   if (labels) {
     SK_TRY(sk_ce_launch(logits, labels, want_dlogits ? wsp<bf16>(lm, w.dlogits) : nullptr, wsp<float>(lm, w.ce_partial),
-                        nullptr, stats, M, T, lm->V, lm->Vp, num_items, dloss, s));
+                        row_nll, stats, M, T, lm->V, lm->Vp, num_items, dloss, s));
   }
   lm->last_B = B;
   lm->last_T = T;
@@ -413,6 +414,29 @@ int sk_lm_set_backward_events(SkLm* lm, void* const* events, int n) {
   lm->bwd_events.assign(n, nullptr);
   for (int i = 0; i < n; ++i) lm->bwd_events[i] = (cudaEvent_t)events[i];
   return 0;
+}
+
+int sk_lm_forward_rows(SkLm* lm, const int64_t* ids, const int64_t* labels, const int32_t* pos_ids, int B, int T,
+                       float* row_nll, float* stats, void* stream) {
+  SK_REQUIRE(lm && ids && labels && row_nll && stats, "sk_lm_forward_rows: null argument");
+  const WsLayout w = make_layout(lm, B, T);
+  SK_TRY(check_bound(lm, B, T, w));
+  return forward_impl(lm, ids, labels, pos_ids, B, T, 1.0f, 1.0f, false, stats, w, (cudaStream_t)stream, row_nll);
+}
+
+int sk_lm_backward_weighted(SkLm* lm, const int64_t* ids, const int64_t* labels, const int32_t* pos_ids, int B, int T,
+                            const float* row_weight, int accumulate, float* stats, void* stream) {
+  SK_REQUIRE(lm && ids && labels && row_weight && stats, "sk_lm_backward_weighted: null argument");
+  SK_REQUIRE(lm->grads, "sk_lm_backward_weighted: no gradient buffer bound");
+  SK_REQUIRE(lm->last_B == B && lm->last_T == T, "sk_lm_backward_weighted: call sk_lm_forward_rows on the same batch first");
+  const WsLayout w = make_layout(lm, B, T);
+  SK_TRY(check_bound(lm, B, T, w));
+  cudaStream_t s = (cudaStream_t)stream;
+  // d loss / d logits[row] = row_weight[row] * (softmax - onehot): recomputed from the logits the forward pass left in
+  // the workspace (num_items = 1, dloss = 1: the caller's weights carry every scale factor)
+  SK_TRY(sk_ce_launch(wsp<bf16>(lm, w.logits), labels, wsp<bf16>(lm, w.dlogits), wsp<float>(lm, w.ce_partial), nullptr,
+                      stats, B * T, T, lm->V, lm->Vp, 1.0f, 1.0f, s, row_weight));
+  return backward_impl(lm, ids, pos_ids, B, T, accumulate, w, s);
 }
 
 const void* sk_lm_logits(const SkLm* lm) {
