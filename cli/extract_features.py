@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch  # noqa: E402
 
-from slamkit_b200.audio_io import load_wav, wav_num_frames  # noqa: E402
+from slamkit_b200.audio_io import audio_num_frames, load_audio  # noqa: E402
 from slamkit_b200.config import load_config, require  # noqa: E402
 
 logger = logging.getLogger(__name__)
@@ -51,7 +51,7 @@ def main(argv=None):
     require(cfg, "data_path", "out_path")
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
-    files = [(f, wav_num_frames(f)) for f in iglob(os.path.join(cfg.data_path, f"**/*.{cfg.ext}"), recursive=True)]
+    files = [(f, audio_num_frames(f)) for f in iglob(os.path.join(cfg.data_path, f"**/*.{cfg.ext}"), recursive=True)]
     files.sort(key=lambda x: x[1], reverse=True)          # WavDataset: sort by duration, longest first
     if cfg.data_skip is not None:
         files = files[cfg.data_skip:]
@@ -67,7 +67,7 @@ def main(argv=None):
         for bi, batch in enumerate(batches):
             if bi % world != rank:
                 continue
-            wavs = [load_wav(f, cfg.sample_rate) for f, _ in batch]
+            wavs = [load_audio(f, cfg.sample_rate) for f, _ in batch]
             lens = torch.tensor([len(w) for w in wavs])
             wav = torch.nn.utils.rnn.pad_sequence(wavs, batch_first=True, padding_value=0)
             reps = tokeniser.audio_represent(wav, lens)

@@ -224,6 +224,14 @@ int sk_kmeans_argmin(const float* dot, const float* centers_sqnorm, int32_t* lab
 /* conv0 statistics buffer length (doubles per clip) */
 int sk_conv0_nstat(void);
 
+/* ---- host-side FLAC decoding (no audio decoder exists in the image) ------------------------------------------------
+ * Replaces torchaudio.info / torchaudio.load in cli/extract_features.py:45-57.  Host pointers. md5_16 receives the
+ * STREAMINFO MD5 of the unencoded audio (all zero if the encoder did not set it). */
+int sk_flac_info(const char* path, int32_t* sample_rate, int32_t* channels, int32_t* bits_per_sample,
+                 int64_t* n_samples, uint8_t* md5_16);
+/* interleaved int32 PCM into a host buffer with room for `capacity` samples per channel */
+int sk_flac_decode_i32(const char* path, int32_t* pcm_host, int64_t capacity, int64_t* n_decoded);
+
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 int64_t sk_launch_count(void);
 /* Bench-only device timing: when enabled, CUDA events are recorded on the launching stream around every launch of
