@@ -153,25 +153,27 @@ __global__ void conv0_affine_kernel(const double* __restrict__ stats, const floa
   affine[(size_t)b * C + c] = make_float2((float)sc, (float)((double)beta[c] - m * sc));
 }
 
-// Pass 2: out[b, t, c] = GELU(conv(x)[c,t] * scale + shift), channels-last, hi/lo bf16.  A thread owns 8 fixed
-// channels (its 8 x KW taps and 8 affine pairs live in registers for the whole kernel) and walks over frames; a warp
-// covers 256 consecutive channels of one frame -> 512-byte coalesced stores per tensor.  No shared memory.
-__global__ void __launch_bounds__(256, 2)
+// Pass 2: out[b, t, c] = GELU(conv(x)[c,t] * scale + shift), channels-last, hi/lo bf16.  A thread owns CPT fixed
+// channels (their CPT x KW taps and affine pairs live in registers for the whole kernel) and walks over frames; a warp
+// covers 32*CPT consecutive channels of one frame (coalesced 8- or 16-byte stores per thread).  No shared memory.
+// CPT = 4 keeps the kernel under 85 registers -> 3 CTAs (24 warps) per SM, which is what hides the MUFU / FMA chains.
+template <int CPT>
+__global__ void __launch_bounds__(256, CPT == 4 ? 3 : 2)
 conv0_apply_kernel(const float* __restrict__ wav, const float* __restrict__ w, const float2* __restrict__ affine,
                    bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int S, int pad, int T0, int C, int KW, int ST) {
   const int b = blockIdx.y;
-  const int groups = C / 8;                       // channel groups of 8 (<= 256)
-  const int lanes_t = blockDim.x / groups;        // frames processed concurrently by a block (>= 1)
+  const int groups = C / CPT;                     // channel groups per frame
+  const int lanes_t = blockDim.x / groups > 0 ? blockDim.x / groups : 1;   // frames processed concurrently by a block
   const int cg = threadIdx.x % groups;
   const int tf = threadIdx.x / groups;
   if (tf >= lanes_t) return;
-  float wr[8][KW_MAX];
-  float2 aff[8];
+  float wr[CPT][KW_MAX];
+  float2 aff[CPT];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    aff[k] = affine[(size_t)b * C + cg * 8 + k];
+  for (int k = 0; k < CPT; ++k) {
+    aff[k] = affine[(size_t)b * C + cg * CPT + k];
 #pragma unroll
-    for (int j = 0; j < KW_MAX; ++j) wr[k][j] = j < KW ? __ldg(w + (cg * 8 + k) * KW + j) : 0.f;
+    for (int j = 0; j < KW_MAX; ++j) wr[k][j] = j < KW ? __ldg(w + (cg * CPT + k) * KW + j) : 0.f;
   }
   const float* wv = wav + (size_t)b * S;
   for (int t = blockIdx.x * lanes_t + tf; t < T0; t += gridDim.x * lanes_t) {
@@ -184,19 +186,34 @@ conv0_apply_kernel(const float* __restrict__ wav, const float* __restrict__ w, c
 #pragma unroll
       for (int j = 0; j < KW_MAX; ++j) x[j] = j < KW ? wav_at(wv, (long)ST * t + j, S, pad) : 0.f;
     }
-    float v[8];
+    float v[CPT];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < CPT; ++k) {
       float y = 0.f;
 #pragma unroll
       for (int j = 0; j < KW_MAX; ++j) y = fmaf(wr[k][j], x[j], y);
       v[k] = gelu_fast(fmaf(y, aff[k].x, aff[k].y));
     }
-    uint4 hi, lo;
-    split8(v, hi, lo);
-    const size_t idx = ((size_t)b * T0 + t) * C + cg * 8;
-    stg128(out_hi + idx, hi);
-    stg128(out_lo + idx, lo);
+    const size_t idx = ((size_t)b * T0 + t) * C + cg * CPT;
+    if (CPT == 8) {
+      float v8[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v8[k] = v[k % CPT];
+      uint4 hi, lo;
+      split8(v8, hi, lo);
+      stg128(out_hi + idx, hi);
+      stg128(out_lo + idx, lo);
+    } else {
+      uint32_t h[CPT / 2], l[CPT / 2];
+#pragma unroll
+      for (int k = 0; k < CPT / 2; ++k) {
+        const float h0 = bf16_round(v[2 * k]), h1 = bf16_round(v[2 * k + 1]);
+        h[k] = pack_bf16(h0, h1);
+        l[k] = pack_bf16(v[2 * k] - h0, v[2 * k + 1] - h1);
+      }
+      *reinterpret_cast<uint2*>(out_hi + idx) = make_uint2(h[0], h[1]);
+      *reinterpret_cast<uint2*>(out_lo + idx) = make_uint2(l[0], l[1]);
+    }
   }
 }
 
@@ -408,7 +425,7 @@ int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const 
                     float2* affine, bf16* out_hi, bf16* out_lo, int B, int S, int pad, int T0, int C, int KW, int ST,
                     float eps, cudaStream_t s) {
   SK_REQUIRE(KW <= KW_MAX, "conv0: kernel width %d > %d", KW, KW_MAX);
-  SK_REQUIRE(C % 8 == 0 && C / 8 <= 256, "conv0: channel count must be a multiple of 8 and <= 2048");
+  SK_REQUIRE(C % 8 == 0 && C / 4 <= 256, "conv0: channel count must be a multiple of 8 and <= 1024");
   SK_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)B * NSTAT * sizeof(double), s));
   dim3 g1(std::min(64, (T0 + 255) / 256), B);
   conv0_stats_kernel<<<g1, 256, 0, s>>>(wav, stats, S, pad, T0, KW, ST);
@@ -416,12 +433,12 @@ int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const 
   dim3 g2((C + 127) / 128, B);
   conv0_affine_kernel<<<g2, 128, 0, s>>>(stats, w, gamma, beta, affine, C, KW, T0, eps);
   SK_LAUNCH_CHECK();
-  const int fpb = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
+  const int fpb = 256 / (C / 4) > 0 ? 256 / (C / 4) : 1;
   int gx = (T0 + fpb - 1) / fpb;
-  const int cap = std::max(1, sk_num_sms() * 4 / B);
+  const int cap = std::max(1, sk_num_sms() * 6 / B);
   if (gx > cap) gx = cap;
   sk_prof_begin(3, s);
-  conv0_apply_kernel<<<dim3(gx, B), 256, 0, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
+  conv0_apply_kernel<4><<<dim3(gx, B), 256, 0, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;
