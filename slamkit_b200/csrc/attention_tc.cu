@@ -303,12 +303,13 @@ int sk_attn_tc_fwd_launch(const bf16* qkv, bf16* o, float* lse, int B, int T, in
 // =================================================================================================
 namespace {
 
+constexpr int BWD_THREADS = 320;                            // TMA warp, MMA warp, 8 element-wise warps (2 per TMEM quadrant)
 constexpr int BQ_BC = 64;                                   // keys per step in the dQ kernel
 constexpr uint32_t T64_BYTES = 64 * 128;                    // [64 rows][64 dims] bf16 tile
 constexpr uint32_t DQ_SMEM = 2 * SQ_BYTES + 4 * T64_BYTES + SQ_BYTES + 256 + 1024;   // Q, dO, K[2], V[2], dS
 
 template <bool CAUSAL>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                       const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
                       const float* __restrict__ delta, bf16* __restrict__ dq, int T, int ldg, int H, int KVH, float scale) {
@@ -341,8 +342,8 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       mbar_init(v_empty + 8 * s, 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_empty, 4);
-    mbar_init(ds_full, 4);
+    mbar_init(sdp_empty, 8);
+    mbar_init(ds_full, 8);
     mbar_init(ds_empty, 1);
     mbar_init(dq_done, 1);
     fence_mbar_init();
@@ -415,7 +416,10 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       }
     }
   } else {
+    // 8 element-wise warps: two per TMEM lane quadrant, each owning one 32-key half of the 64-key tile (P and dS are
+    // purely element-wise given lse / delta, so the halves never need to talk to each other)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int qrow = q0 + r;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -428,42 +432,36 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       const int k0 = j * BQ_BC;
       mbar_wait(sdp_full, j & 1);
       tc_fence_after();
-      uint32_t sv[2][32], dv[2][32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tmem_ld_32(tS + lane_off + c * 32, sv[c]);
-        tmem_ld_32(tdP + lane_off + c * 32, dv[c]);
-      }
+      uint32_t sv[32], dv[32];
+      tmem_ld_32(tS + lane_off + half * 32, sv);
+      tmem_ld_32(tdP + lane_off + half * 32, dv);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
       const bool need_mask = (CAUSAL && k0 + BQ_BC - 1 > q0) || (k0 + BQ_BC > T) || (q0 + AT_BR > T);
       mbar_wait(ds_empty, (j & 1) ^ 1u);         // previous dQ MMA finished reading the dS buffer
+      uint32_t pk[16];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * i]), sl2, -lse2));
-          float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * i + 1]), sl2, -lse2));
-          if (need_mask) {
-            const int key = k0 + c * 32 + 2 * i;
-            if (!row_ok || key >= T || (CAUSAL && key > qrow)) p0 = 0.f;
-            if (!row_ok || key + 1 >= T || (CAUSAL && key + 1 > qrow)) p1 = 0.f;
-          }
-          const float d0 = p0 * (__uint_as_float(dv[c][2 * i]) - del) * scale;
-          const float d1 = p1 * (__uint_as_float(dv[c][2 * i + 1]) - del) * scale;
-          pk[i] = pack_bf16(d0, d1);
+      for (int i = 0; i < 16; ++i) {
+        float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), sl2, -lse2));
+        float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -lse2));
+        if (need_mask) {
+          const int key = k0 + half * 32 + 2 * i;
+          if (!row_ok || key >= T || (CAUSAL && key > qrow)) p0 = 0.f;
+          if (!row_ok || key + 1 >= T || (CAUSAL && key + 1 > qrow)) p1 = 0.f;
         }
+        const float d0 = p0 * (__uint_as_float(dv[2 * i]) - del) * scale;
+        const float d1 = p1 * (__uint_as_float(dv[2 * i + 1]) - del) * scale;
+        pk[i] = pack_bf16(d0, d1);
+      }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int chunk = c * 4 + u;           // 8 chunks of 8 keys in the 64-key row
-          const uint32_t dst = sdS + r * 128 + ((chunk ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
-                       "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
-                       : "memory");
-        }
+      for (int u = 0; u < 4; ++u) {
+        const int chunk = half * 4 + u;          // 8 chunks of 8 keys in the 64-key row
+        const uint32_t dst = sdS + r * 128 + ((chunk ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
+                     "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+                     : "memory");
       }
       fence_proxy_async();
       __syncwarp();
@@ -472,10 +470,9 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     mbar_wait(dq_done, 0);
     tc_fence_after();
     bf16* op = dq + ((size_t)(row_base + qrow)) * ldg + h * 64;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld_32(tdQ + lane_off + c * 32, v);
+      tmem_ld_32(tdQ + lane_off + half * 32, v);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
@@ -485,7 +482,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           w.y = pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3]));
           w.z = pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]));
           w.w = pack_bf16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]));
-          stg128(op + c * 32 + u * 8, w);
+          stg128(op + half * 32 + u * 8, w);
         }
       }
     }
@@ -498,12 +495,11 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   }
 }
 
-
 constexpr int BK_BR = 64;                                   // query rows per step in the dK/dV kernel
 constexpr uint32_t DKDV_SMEM = 2 * SKV_BYTES + 4 * T64_BYTES + 2 * SKV_BYTES + 2 * 2 * 64 * 4 + 256 + 1024;
 
 template <bool CAUSAL>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                         const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
                         const float* __restrict__ delta, float* __restrict__ partial /*[B][H][T][128]*/, int T, int H,
@@ -536,8 +532,8 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       mbar_init(q_empty + 8 * s, 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_empty, 4);
-    mbar_init(pds_full, 4);
+    mbar_init(sdp_empty, 8);
+    mbar_init(pds_full, 8);
     mbar_init(pds_empty, 1);
     mbar_init(acc_done, 1);
     fence_mbar_init();
@@ -610,64 +606,59 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;            // which 32-query half of the 64-query tile this warp handles
     const int r = q * 32 + lane;                 // key row inside the tile == TMEM lane
     const int key = k0 + r;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float sl2 = scale * 1.4426950408889634f;
-    const int tid = threadIdx.x - 64;            // 0..127 among the softmax warps
+    const int tid = threadIdx.x - 64;            // 0..255 among the element-wise warps
     for (int i = 0; i < n_it; ++i) {
       const int q0 = (qt_begin + i) * BK_BR;
       // stage the 64 lse / delta values of this query tile (per-COLUMN quantities here) in smem
       float* st_lse = stat_ptr + (i & 1) * 128;
-      {
+      if (tid < 128) {
         const int qq = q0 + (tid & 63);
         const size_t off = ((size_t)b * H + h) * T + (qq < T ? qq : 0);
         const float val = qq < T ? ((tid < 64) ? lse[off] * 1.4426950408889634f : delta[off]) : 0.f;
         st_lse[tid] = val;                       // [0,64): lse * log2e, [64,128): delta
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
-      uint32_t sv[2][32], dv[2][32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tmem_ld_32(tST + lane_off + c * 32, sv[c]);
-        tmem_ld_32(tdPT + lane_off + c * 32, dv[c]);
-      }
+      uint32_t sv[32], dv[32];
+      tmem_ld_32(tST + lane_off + half * 32, sv);
+      tmem_ld_32(tdPT + lane_off + half * 32, dv);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
       const bool need_mask = (CAUSAL && q0 < k0 + AT_BC) || (q0 + BK_BR > T) || (k0 + AT_BC > T);
       mbar_wait(pds_empty, (i & 1) ^ 1u);        // previous dV / dK MMAs finished reading P^T / dS^T
+      uint32_t pp[16], pd[16];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pp[16], pd[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int qi = c * 32 + 2 * e;
-          const float2 l2 = *reinterpret_cast<const float2*>(st_lse + qi);
-          const float2 dl = *reinterpret_cast<const float2*>(st_lse + 64 + qi);
-          float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * e]), sl2, -l2.x));
-          float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * e + 1]), sl2, -l2.y));
-          if (need_mask) {
-            const int qrow = q0 + qi;
-            if (key >= T || qrow >= T || (CAUSAL && key > qrow)) p0 = 0.f;
-            if (key >= T || qrow + 1 >= T || (CAUSAL && key > qrow + 1)) p1 = 0.f;
-          }
-          pp[e] = pack_bf16(p0, p1);
-          pd[e] = pack_bf16(p0 * (__uint_as_float(dv[c][2 * e]) - dl.x) * scale,
-                            p1 * (__uint_as_float(dv[c][2 * e + 1]) - dl.y) * scale);
+      for (int e = 0; e < 16; ++e) {
+        const int qi = half * 32 + 2 * e;
+        const float2 l2 = *reinterpret_cast<const float2*>(st_lse + qi);
+        const float2 dl = *reinterpret_cast<const float2*>(st_lse + 64 + qi);
+        float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), sl2, -l2.x));
+        float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), sl2, -l2.y));
+        if (need_mask) {
+          const int qrow = q0 + qi;
+          if (key >= T || qrow >= T || (CAUSAL && key > qrow)) p0 = 0.f;
+          if (key >= T || qrow + 1 >= T || (CAUSAL && key > qrow + 1)) p1 = 0.f;
         }
+        pp[e] = pack_bf16(p0, p1);
+        pd[e] = pack_bf16(p0 * (__uint_as_float(dv[2 * e]) - dl.x) * scale,
+                          p1 * (__uint_as_float(dv[2 * e + 1]) - dl.y) * scale);
+      }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int chunk = c * 4 + u;
-          const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPT + off), "r"(pp[4 * u]), "r"(pp[4 * u + 1]),
-                       "r"(pp[4 * u + 2]), "r"(pp[4 * u + 3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdST + off), "r"(pd[4 * u]), "r"(pd[4 * u + 1]),
-                       "r"(pd[4 * u + 2]), "r"(pd[4 * u + 3]) : "memory");
-        }
+      for (int u = 0; u < 4; ++u) {
+        const int chunk = half * 4 + u;
+        const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPT + off), "r"(pp[4 * u]), "r"(pp[4 * u + 1]),
+                     "r"(pp[4 * u + 2]), "r"(pp[4 * u + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdST + off), "r"(pd[4 * u]), "r"(pd[4 * u + 1]),
+                     "r"(pd[4 * u + 2]), "r"(pd[4 * u + 3]) : "memory");
       }
       fence_proxy_async();
       __syncwarp();
@@ -680,7 +671,7 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     }
     float* pp = partial + (((size_t)b * H + h) * T + key) * 128;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {               // columns 0..63 = dK (TMEM 128..191), 64..127 = dV (192..255)
+    for (int c = half * 2; c < half * 2 + 2; ++c) {   // columns 0..63 = dK (TMEM 128..191), 64..127 = dV (192..255)
       uint32_t v[32];
       if (n_it > 0) {
         tmem_ld_32(tdK + lane_off + c * 32, v);
@@ -759,11 +750,11 @@ int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const
   bf16* dk = dqkv + H * 64;
   bf16* dv = dqkv + (H + KVH) * 64;
   if (causal) {
-    attn_tc_bwd_dkdv_kernel<true><<<g1, AT_THREADS, DKDV_SMEM, s>>>(tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale);
-    attn_tc_bwd_dq_kernel<true><<<g2, AT_THREADS, DQ_SMEM, s>>>(tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale);
+    attn_tc_bwd_dkdv_kernel<true><<<g1, BWD_THREADS, DKDV_SMEM, s>>>(tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale);
+    attn_tc_bwd_dq_kernel<true><<<g2, BWD_THREADS, DQ_SMEM, s>>>(tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale);
   } else {
-    attn_tc_bwd_dkdv_kernel<false><<<g1, AT_THREADS, DKDV_SMEM, s>>>(tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale);
-    attn_tc_bwd_dq_kernel<false><<<g2, AT_THREADS, DQ_SMEM, s>>>(tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale);
+    attn_tc_bwd_dkdv_kernel<false><<<g1, BWD_THREADS, DKDV_SMEM, s>>>(tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale);
+    attn_tc_bwd_dq_kernel<false><<<g2, BWD_THREADS, DQ_SMEM, s>>>(tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale);
   }
   const long total = (long)B * KVH * T * 16;
   int blocks = (int)((total + 255) / 256);

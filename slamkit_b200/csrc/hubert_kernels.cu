@@ -167,17 +167,18 @@ conv0_apply_kernel(const float* __restrict__ wav, const float* __restrict__ w, c
   const int cg = threadIdx.x % groups;
   const int tf = threadIdx.x / groups;
   if (tf >= lanes_t) return;
+  // GroupNorm's per-(clip, channel) scale is folded into the taps, its shift seeds the accumulator
   float wr[CPT][KW_MAX];
-  float2 aff[CPT];
+  float sh[CPT];
 #pragma unroll
   for (int k = 0; k < CPT; ++k) {
-    aff[k] = affine[(size_t)b * C + cg * CPT + k];
+    const float2 a = affine[(size_t)b * C + cg * CPT + k];
+    sh[k] = a.y;
 #pragma unroll
-    for (int j = 0; j < KW_MAX; ++j) wr[k][j] = j < KW ? __ldg(w + (cg * CPT + k) * KW + j) : 0.f;
+    for (int j = 0; j < KW_MAX; ++j) wr[k][j] = j < KW ? __ldg(w + (cg * CPT + k) * KW + j) * a.x : 0.f;
   }
   const float* wv = wav + (size_t)b * S;
-  for (int t = blockIdx.x * lanes_t + tf; t < T0; t += gridDim.x * lanes_t) {
-    float x[KW_MAX];
+  auto load_x = [&](int t, float (&x)[KW_MAX]) {
     const long i0 = (long)ST * t - pad;          // first waveform sample of this frame (before the (pad,pad) padding)
     if (i0 >= 0 && i0 + KW_MAX <= S) {           // interior frame: no bounds checks
 #pragma unroll
@@ -186,13 +187,23 @@ conv0_apply_kernel(const float* __restrict__ wav, const float* __restrict__ w, c
 #pragma unroll
       for (int j = 0; j < KW_MAX; ++j) x[j] = j < KW ? wav_at(wv, (long)ST * t + j, S, pad) : 0.f;
     }
+  };
+  const int t_step = gridDim.x * lanes_t;
+  int t = blockIdx.x * lanes_t + tf;
+  float xn[KW_MAX];
+  if (t < T0) load_x(t, xn);
+  for (; t < T0; t += t_step) {
+    float x[KW_MAX];
+#pragma unroll
+    for (int j = 0; j < KW_MAX; ++j) x[j] = xn[j];
+    if (t + t_step < T0) load_x(t + t_step, xn);   // prefetch the next frame's window: hides the global-load latency
     float v[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
-      float y = 0.f;
+      float y = sh[k];
 #pragma unroll
       for (int j = 0; j < KW_MAX; ++j) y = fmaf(wr[k][j], x[j], y);
-      v[k] = gelu_fast(fmaf(y, aff[k].x, aff[k].y));
+      v[k] = gelu_fast(y);
     }
     const size_t idx = ((size_t)b * T0 + t) * C + cg * CPT;
     if (CPT == 8) {
@@ -433,12 +444,12 @@ int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const 
   dim3 g2((C + 127) / 128, B);
   conv0_affine_kernel<<<g2, 128, 0, s>>>(stats, w, gamma, beta, affine, C, KW, T0, eps);
   SK_LAUNCH_CHECK();
-  const int fpb = 256 / (C / 4) > 0 ? 256 / (C / 4) : 1;
+  const int fpb = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
   int gx = (T0 + fpb - 1) / fpb;
-  const int cap = std::max(1, sk_num_sms() * 6 / B);
+  const int cap = std::max(1, sk_num_sms() * 4 / B);
   if (gx > cap) gx = cap;
   sk_prof_begin(3, s);
-  conv0_apply_kernel<4><<<dim3(gx, B), 256, 0, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
+  conv0_apply_kernel<8><<<dim3(gx, B), 256, 0, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;
