@@ -292,6 +292,265 @@ int sk_attn_tc_fwd_launch(const bf16* qkv, bf16* o, float* lse, int B, int T, in
 }
 
 // =================================================================================================
+// Split-precision (hi, lo) bidirectional forward for the HuBERT encoder on tcgen05: same pipeline as attn_tc_fwd_kernel,
+// but every operand is a bf16 (hi, lo) pair and each product is three MMAs into the same TMEM accumulator
+//   S = Ql Kh^T + Qh Kl^T + Qh Kh^T ,   O += Pl Vh + Ph Vl + Ph Vh        (fp32-grade, see hubert_kernels.cu)
+// One CTA per SM (192 KB of operand tiles); S_{j+1} is issued while the softmax warps work on tile j.
+// =================================================================================================
+namespace {
+
+constexpr uint32_t ATS_SMEM = 2 * SQ_BYTES + 4 * SKV_BYTES + 2 * SKV_BYTES + 2 * SP_BYTES + 256 + 1024;   // ~193 KB
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_fwd_split_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL,
+                         bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, int T, int ldo, int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQh = smem_base, sQl = sQh + SQ_BYTES;
+  const uint32_t sK = sQl + SQ_BYTES;            // stage s: Kh at sK + s*32K, Kl at +16K
+  const uint32_t sVh = sK + 4 * SKV_BYTES, sVl = sVh + SKV_BYTES;
+  const uint32_t sPh = sVl + SKV_BYTES, sPl = sPh + SP_BYTES;
+  const uint32_t bar = sPl + SP_BYTES;
+  const uint32_t q_full = bar, k_full = bar + 8 /*[2]*/, k_empty = bar + 24 /*[2]*/, v_full = bar + 40, v_empty = bar + 48,
+                 s_full = bar + 56, s_empty = bar + 64, p_full = bar + 72, o_done = bar + 80, tmem_slot = bar + 88;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = (int)blockIdx.x * AT_BR;
+  const int row_base = b * T;
+  const int n_kv = (T + AT_BC - 1) / AT_BC;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmH);
+    tma_prefetch_desc(&tmL);
+    mbar_init(q_full, 1);
+    mbar_init(k_full, 1);
+    mbar_init(k_full + 8, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(k_empty + 8, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * SQ_BYTES);
+      tma_load_2d(sQh, &tmH, q_full, h * 64, row_base + q0);
+      tma_load_2d(sQl, &tmL, q_full, h * 64, row_base + q0);
+      auto load_v = [&](int j) {
+        mbar_wait_sleep(v_empty, (j & 1) ^ 1u);
+        mbar_arrive_expect_tx(v_full, 2 * SKV_BYTES);
+        tma_load_2d(sVh, &tmH, v_full, (2 * H + h) * 64, row_base + j * AT_BC);
+        tma_load_2d(sVl, &tmL, v_full, (2 * H + h) * 64, row_base + j * AT_BC);
+      };
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait_sleep(k_empty + 8 * st, ((j >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(k_full + 8 * st, 2 * SKV_BYTES);
+        tma_load_2d(sK + st * 2 * SKV_BYTES, &tmH, k_full + 8 * st, (H + h) * 64, row_base + j * AT_BC);
+        tma_load_2d(sK + st * 2 * SKV_BYTES + SKV_BYTES, &tmL, k_full + 8 * st, (H + h) * 64, row_base + j * AT_BC);
+        if (j >= 1) load_v(j - 1);
+      }
+      load_v(n_kv - 1);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(1u, 0u, 0u, 128, 128);
+      constexpr uint32_t idesc_o = umma_idesc(1u, 0u, 1u, 128, 64);
+      auto issue_s = [&](int j) {
+        const uint32_t kh = sK + (j & 1) * 2 * SKV_BYTES, kl = kh + SKV_BYTES;
+        const uint32_t qa[3] = {sQl, sQh, sQh};      // small terms first
+        const uint32_t kb[3] = {kh, kl, kh};
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16(tS, umma_desc_sw128(qa[t] + k * 32, 16, 1024), umma_desc_sw128(kb[t] + k * 32, 16, 1024), idesc_s,
+                       (t > 0 || k > 0) ? 1u : 0u);
+        tc_commit(s_full);
+        tc_commit(k_empty + 8 * (j & 1));
+      };
+      mbar_wait_sleep(q_full, 0);
+      mbar_wait_sleep(k_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {
+          mbar_wait_sleep(k_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
+          mbar_wait_sleep(s_empty, j & 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait_sleep(p_full, j & 1);
+        mbar_wait_sleep(v_full, j & 1);
+        tc_fence_after();
+        const uint32_t pa[3] = {sPl, sPh, sPh};
+        const uint32_t vb[3] = {sVh, sVl, sVh};
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            tc_mma_f16(tO, umma_desc_sw128(pa[t] + (k >> 2) * (AT_BR * 128) + (k & 3) * 32, 16, 1024),
+                       umma_desc_sw128(vb[t] + k * 2048, 8192, 1024), idesc_o, (j > 0 || t > 0 || k > 0) ? 1u : 0u);
+        tc_commit(v_empty);
+        tc_commit(o_done);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int qrow = q0 + r;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float sl2 = scale * 1.4426950408889634f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int k0 = j * AT_BC;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t v[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32(tS + lane_off + c * 32, v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+      if (k0 + AT_BC > T) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (k0 + c * 32 + i >= T) v[c][i] = 0xff800000u;
+      }
+      float mx = m_run;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c][i]));
+      const float m_new = mx;
+      const float mb = m_new * sl2;
+      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * sl2 - mb);
+      if (j > 0) {
+        mbar_wait(o_done, (j - 1) & 1);
+        tc_fence_after();
+      }
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          // exp2f (not the approx form): this path must stay fp32-grade
+          const float p0 = exp2f(fmaf(__uint_as_float(v[c][2 * i]), sl2, -mb));
+          const float p1 = exp2f(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, -mb));
+          rs0 += p0;
+          rs1 += p1;
+          const float h0 = bf16_round(p0), h1 = bf16_round(p1);
+          ph[i] = pack_bf16(h0, h1);
+          pl[i] = pack_bf16(p0 - h0, p1 - h1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int chunk = c * 4 + u;
+          const uint32_t off = (chunk >> 3) * (AT_BR * 128) + r * 128 + (((chunk & 7) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPh + off), "r"(ph[4 * u]), "r"(ph[4 * u + 1]),
+                       "r"(ph[4 * u + 2]), "r"(ph[4 * u + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPl + off), "r"(pl[4 * u]), "r"(pl[4 * u + 1]),
+                       "r"(pl[4 * u + 2]), "r"(pl[4 * u + 3]) : "memory");
+        }
+      }
+      l_run = l_run * alpha + (rs0 + rs1);
+      m_run = m_new;
+      if (j > 0) {
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t w[32];
+            tmem_ld_32(tO + lane_off + c * 32, w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) * alpha);
+            tmem_st_32(tO + lane_off + c * 32, w);
+          }
+          tmem_st_wait();
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(o_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    const size_t off = ((size_t)(row_base + qrow)) * ldo + h * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t w[32];
+      tmem_ld_32(tO + lane_off + c * 32, w);
+      tmem_ld_wait();
+      if (qrow < T) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t hh[4], ll[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a0 = __uint_as_float(w[8 * u + 2 * e]) * inv, a1 = __uint_as_float(w[8 * u + 2 * e + 1]) * inv;
+            const float h0 = bf16_round(a0), h1 = bf16_round(a1);
+            hh[e] = pack_bf16(h0, h1);
+            ll[e] = pack_bf16(a0 - h0, a1 - h1);
+          }
+          stg128(o_hi + off + c * 32 + u * 8, make_uint4(hh[0], hh[1], hh[2], hh[3]));
+          stg128(o_lo + off + c * 32 + u * 8, make_uint4(ll[0], ll[1], ll[2], ll[3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace
+
+// qkv_hi / qkv_lo: [B*T, ld] with H q-heads, H k-heads, H v-heads (64 columns each); o_hi / o_lo: [B*T, ldo]
+int sk_attn_tc_fwd_split_launch(const bf16* qkv_hi, const bf16* qkv_lo, bf16* o_hi, bf16* o_lo, int B, int T, int H, int ld,
+                                int ldo, float scale, cudaStream_t s) {
+  SK_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "attention: leading dims must be multiples of 8");
+  CUtensorMap th, tl;
+  int rc;
+  if ((rc = sk_make_tmap_2d(&th, qkv_hi, 2, (uint64_t)3 * H * 64, (uint64_t)B * T, (uint64_t)ld, 64, 128))) return rc;
+  if ((rc = sk_make_tmap_2d(&tl, qkv_lo, 2, (uint64_t)3 * H * 64, (uint64_t)B * T, (uint64_t)ld, 64, 128))) return rc;
+  static bool init = false;
+  if (!init) {
+    SK_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM));
+    init = true;
+  }
+  dim3 grid((T + AT_BR - 1) / AT_BR, H, B);
+  sk_prof_begin(1, s);
+  attn_tc_fwd_split_kernel<<<grid, AT_THREADS, ATS_SMEM, s>>>(th, tl, o_hi, o_lo, T, ldo, H, scale);
+  sk_prof_end(s);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
 // Backward on tcgen05.  Two deterministic kernels like the warp-level version (no atomics):
 //   dQ    : CTA = (128-query tile, head, batch), loops over 64-key tiles; S and dP accumulate in TMEM, the thread that
 //           owns a query row turns them into dS (bf16, swizzled smem), dQ += dS K on the tensor pipe.

@@ -13,6 +13,7 @@
 #include <vector>
 #include <string.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 constexpr int64_t ALIGN_ELEMS = 64;
@@ -45,6 +46,7 @@ struct SkHubert {
   float* csq = nullptr;
   uint8_t* ws = nullptr;
   int64_t ws_bytes = 0;
+  int attn_tc = 1;   // tcgen05 split-precision attention (SK_HUBERT_ATTN_TC=0 selects the warp-level kernel)
 };
 
 namespace {
@@ -210,8 +212,11 @@ int forward_impl(SkHubert* h, const float* wav, const int64_t* lens, int B, int 
     const LayerOff& o = h->lo[l];
     const bool last = (l == h->cfg.n_layers - 1) || (dbg_stage == l + 1);
     SK_TRY(linear_split(h, M, 3 * H, H, hb[0], o.wqkv, o.bqkv, 0, nullptr, qkv, nullptr, 3 * H, s));
-    SK_TRY(sk_attn_fwd_split_launch(qkv.hi, qkv.lo, qkv.hi + H, qkv.lo + H, qkv.hi + 2 * H, qkv.lo + 2 * H, ao.hi, ao.lo, B,
-                                    Tf, h->cfg.n_heads, 3 * H, H, scale, s));
+    if (h->attn_tc)
+      SK_TRY(sk_attn_tc_fwd_split_launch(qkv.hi, qkv.lo, ao.hi, ao.lo, B, Tf, h->cfg.n_heads, 3 * H, H, scale, s));
+    else
+      SK_TRY(sk_attn_fwd_split_launch(qkv.hi, qkv.lo, qkv.hi + H, qkv.lo + H, qkv.hi + 2 * H, qkv.lo + 2 * H, ao.hi, ao.lo,
+                                      B, Tf, h->cfg.n_heads, 3 * H, H, scale, s));
     SK_TRY(linear_split(h, M, H, H, ao, o.wo, o.bo, 0, &hb[0], t1, nullptr, H, s));
     SK_TRY(sk_layernorm_hilo_launch(t1.hi, t1.lo, nullptr, nullptr, h->w32 + o.ln1g, h->w32 + o.ln1b, hb[1].hi, hb[1].lo,
                                     nullptr, M, H, eps, s));
@@ -247,6 +252,7 @@ int sk_hubert_create(const SkHubertConfig* cfg, SkHubert** out) {
   SK_REQUIRE(cfg->pos_conv_kernel % 2 == 0, "sk_hubert_create: only even positional-conv kernels (HF drops the last frame)");
   SkHubert* h = new SkHubert();
   h->cfg = *cfg;
+  if (const char* e = getenv("SK_HUBERT_ATTN_TC")) h->attn_tc = atoi(e);
   h->C = cfg->conv_dim; h->H = cfg->hidden; h->F = cfg->ffn;
   h->G = cfg->pos_conv_groups; h->cg = cg; h->Kpos = cfg->pos_conv_kernel; h->halo = cfg->pos_conv_kernel / 2;
   h->U = cfg->n_units; h->Upad = (cfg->n_units + 63) / 64 * 64;

@@ -73,6 +73,8 @@ int sk_attn_fwd_split_launch(const bf16* q_hi, const bf16* q_lo, const bf16* k_h
                              cudaStream_t s);
 
 // attention_tc.cu (tcgen05 / TMEM flash attention)
+int sk_attn_tc_fwd_split_launch(const bf16* qkv_hi, const bf16* qkv_lo, bf16* o_hi, bf16* o_lo, int B, int T, int H, int ld,
+                                int ldo, float scale, cudaStream_t s);
 int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse, float* delta, float* partial,
                           bf16* dqkv, int B, int T, int H, int KVH, int ld, int ldo, int ldg, int causal, float scale,
                           cudaStream_t s);

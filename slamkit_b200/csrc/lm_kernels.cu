@@ -217,22 +217,25 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
   }
 }
 
-// out[j] = bf16( (accumulate ? out[j] : 0) + sum_b partial[b][j] ).  Block = 32 columns x 8 row groups; rows are
-// summed in a fixed order (deterministic), 128-byte coalesced reads per warp.
-__global__ void __launch_bounds__(256)
+// out[j] = bf16( (accumulate ? out[j] : 0) + sum_b partial[b][j] ).  Block = 32 columns x 32 row groups (1024 threads);
+// every thread sums a fixed strided subset of rows, then a fixed-order tree over the 32 groups (deterministic).
+__global__ void __launch_bounds__(1024)
 colsum_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int nblocks, int D, int accumulate) {
-  __shared__ float sred[8][33];
+  __shared__ float sred[32][33];
   const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + c;
   float s = 0.f;
   if (j < D)
-    for (int b = rg; b < nblocks; b += 8) s += partial[(size_t)b * D + j];
+    for (int b = rg; b < nblocks; b += 32) s += partial[(size_t)b * D + j];
   sred[rg][c] = s;
   __syncthreads();
-  if (rg == 0 && j < D) {
-    float t = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += sred[r][c];
+  for (int st = 16; st > 0; st >>= 1) {
+    if (rg < st) sred[rg][c] += sred[rg + st][c];
+    __syncthreads();
+  }
+  if (rg == 0 && j < D) {
+    float t = sred[0][c];
     if (accumulate) t += __bfloat162float(out[j]);
     out[j] = __float2bfloat16_rn(t);
   }
@@ -649,7 +652,7 @@ int sk_rmsnorm_bwd_launch(const bf16* dy, const bf16* x, const bf16* w, const fl
   const size_t smem = (size_t)WARPS_PER_BLOCK * D * sizeof(float);
   rmsnorm_bwd_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, s>>>(dy, x, w, rstd, dres, dx, dw_partial, M, D);
   SK_LAUNCH_CHECK();
-  colsum_reduce_kernel<<<(D + 31) / 32, 256, 0, s>>>(dw_partial, dw, blocks, D, accumulate_dw);
+  colsum_reduce_kernel<<<(D + 31) / 32, 1024, 0, s>>>(dw_partial, dw, blocks, D, accumulate_dw);
   SK_LAUNCH_CHECK();
   return 0;
 }
@@ -660,7 +663,7 @@ int sk_colsum_launch(const bf16* x, bf16* out, float* partial, int M, int N, int
   dim3 grid((N / 8 + 127) / 128, COLSUM_SPLITS);
   colsum_partial_kernel<<<grid, 128, 0, s>>>(x, partial, M, N, ld);
   SK_LAUNCH_CHECK();
-  colsum_reduce_kernel<<<(N + 31) / 32, 256, 0, s>>>(partial, out, COLSUM_SPLITS, N, accumulate);
+  colsum_reduce_kernel<<<(N + 31) / 32, 1024, 0, s>>>(partial, out, COLSUM_SPLITS, N, accumulate);
   SK_LAUNCH_CHECK();
   return 0;
 }
