@@ -47,6 +47,15 @@ int sk_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const vo
 int sk_gemm_bf16_splitk(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                         int ldc, int accumulate, void* splitk_ws, int64_t splitk_ws_bytes, void* stream);
 
+/* General form with a scratch buffer.  With ws_bytes >= sk_gemm_ws_bytes() the launch is load-balanced stream-K style:
+ * the K loops of the tiles that would form a last, partial wave are laid end to end and cut evenly over all SMs, fp32
+ * partial tiles meet in the scratch and are added in a fixed order (deterministic, bit-identical run to run).  The last 4096 bytes of the scratch are flag words: they must be zero before
+ * the first call and are left zero by every call.  One scratch buffer serves one stream at a time. */
+int sk_gemm_bf16_ws(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                    int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
+                    int force_bn, void* ws, int64_t ws_bytes, void* stream);
+int64_t sk_gemm_ws_bytes(void);
+
 /* ---- causal-LM element-wise / reduction kernels (path (ii)) --------------------------------------------------- */
 /* Embedding lookup, HF:models/qwen2/modeling_qwen2.py:332-415 (embed_tokens). ids int64 [M]. */
 int sk_embed_fwd(const int64_t* ids, const void* table, void* out, int M, int D, int V, void* stream);

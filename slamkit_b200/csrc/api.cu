@@ -107,6 +107,15 @@ int sk_gemm_bf16_splitk(int M, int N, int K, const void* A, int lda, int a_mn, c
   return sk_gemm_launch(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, 0, nullptr, accumulate ? C : nullptr, ldc, 1, 0, 0,
                         S(stream), splitk_ws, (size_t)splitk_ws_bytes);
 }
+int sk_gemm_bf16_ws(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                    int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
+                    int force_bn, void* ws, int64_t ws_bytes, void* stream) {
+  SK_REQUIRE(A && B && C, "sk_gemm_bf16_ws: null operand");
+  SK_REQUIRE(ws == nullptr || (((uintptr_t)ws & 15) == 0 && ws_bytes % 16 == 0), "sk_gemm_bf16_ws: scratch must be 16-byte aligned");
+  return sk_gemm_launch(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, out_f32, bias, residual, ldr, round_before_res, act,
+                        force_bn, S(stream), ws, (size_t)ws_bytes);
+}
+int64_t sk_gemm_ws_bytes(void) { return (int64_t)sk_gemm_ws_min_bytes(); }
 int sk_embed_fwd(const int64_t* ids, const void* table, void* out, int M, int D, int V, void* stream) {
   return sk_embed_fwd_launch(ids, CBF(table), BF(out), M, D, V, S(stream));
 }

@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace {
@@ -49,14 +50,22 @@ struct GemmParams {
   int splits;           // > 1: split-K; work item = (tile, split), fp32 partial tiles go to splitk_ws[split][M][N]
   float* splitk_ws;
   int tma_store;        // 1: bf16 output leaves through swizzled smem staging + cp.async.bulk.tensor stores (tmC)
+  int sk_units;         // > 0: stream-K over the first sk_units tile groups ("units", see WorkIter)
+  int sk_groups;        // CTA groups that share the stream-K iteration space (each unit is cut into <= ~4 ranges)
+  int sk_G;             // tiles per unit = CTAs per group (they run the same k-blocks in lockstep)
+  int sk_colunits;      // 0: a unit is one row of tiles (same A rows);  1: one column of tiles (same B rows)
+  int units, n_groups;  // total units, CTA groups in the grid
+  float* sk_ws;         // stream-K partial tiles, one 128 x 256 fp32 slot per CTA
+  uint32_t* sk_flags;   // [grid][4] publish flags (per epilogue warp), zero between launches
 };
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ATOMS = (BN + 63) / 64;            // MN-major B is fetched in 64-column atoms
+  static constexpr int B_BYTES = B_ATOMS * 64 * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int STAGES = (BN > 128) ? 4 : (BN > 64 ? 6 : 8);
   static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int STAGING_BYTES = 4 * 2 * 4096;  // per epilogue warp: 2 x (32 rows x 128 B) TMA-store buffers
@@ -66,7 +75,197 @@ struct GemmCfg {
 
 SK_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN, bool A_MN, bool B_MN>
+// Work scheduler shared by the three warp roles.
+//
+// Plain mode (p.sk_units == 0): work item i = blockIdx.x + k * gridDim.x is a whole tile (or a legacy split-K slice).
+//
+// Stream-K mode: tiles are grouped into "units" of G tiles that read the same rows of the large operand (a row of
+// output tiles shares A, a column shares B) and CTAs into groups of G; member j of a group always works on tile j of
+// the group's unit, so the G CTAs walk the same k-blocks together and the shared operand is fetched from HBM once
+// (what whole-tile scheduling gets for free from running adjacent tiles in the same wave).  The units that would form
+// the last, partial wave have their K loops laid end to end and cut into p.sk_groups equal ranges; a range touches at
+// most two units.  role 1 = the range starts inside a unit: the fp32 partial tile goes to the CTA's scratch slot;
+// role 2 = the range holds the unit's first k-block but not its last: this CTA finishes the tile and adds the partials
+// of the same member of the following groups in a fixed order (deterministic); role 0 = whole tile.  The remaining
+// units are processed whole, after the stream-K ranges, so the fix-up of a tile overlaps the next tile's MMAs.
+template <bool SK>
+struct WorkIter {
+  int num_kb, splits, kb_per_split, total_items, tiles_n;
+  // stream-K
+  int G, colunits, units, n_groups, sk_groups, grp, mem;
+  long sk_total, sk_cur, sk_end;
+  int next_unit, next_item;
+  // current item
+  int tile, split, kb_begin, kb_end, role;
+  long unit_end_it;
+  SK_DEVINL WorkIter(const GemmParams& p, int num_kb_, int kb_per_split_, int total_items_) {
+    num_kb = num_kb_;
+    splits = p.splits;
+    kb_per_split = kb_per_split_;
+    total_items = total_items_;
+    tiles_n = p.tiles_n;
+    G = p.sk_G;
+    colunits = p.sk_colunits;
+    units = p.units;
+    n_groups = p.n_groups;
+    sk_groups = p.sk_groups;
+    tile = split = kb_begin = kb_end = role = 0;
+    unit_end_it = 0;
+    sk_total = sk_cur = sk_end = 0;
+    next_item = (int)blockIdx.x;
+    next_unit = 0;
+    grp = mem = 0;
+    if (SK && p.sk_units > 0) {
+      grp = (int)blockIdx.x / G;
+      mem = (int)blockIdx.x - grp * G;
+      next_item = total_items;                               // plain mode off
+      next_unit = grp < n_groups ? p.sk_units + grp : units; // CTAs past the last full group stay idle
+      if (grp < sk_groups) {
+        sk_total = (long)p.sk_units * num_kb;
+        sk_cur = sk_total * grp / sk_groups;
+        sk_end = sk_total * (grp + 1) / sk_groups;
+      }
+    }
+  }
+  SK_DEVINL int tile_of(int unit) const { return colunits ? mem * tiles_n + unit : unit * G + mem; }
+  SK_DEVINL bool next() {
+    if (SK && sk_cur < sk_end) {
+      const int unit = (int)(sk_cur / num_kb);
+      kb_begin = (int)(sk_cur - (long)unit * num_kb);
+      unit_end_it = (long)(unit + 1) * num_kb;
+      const long e = sk_end < unit_end_it ? sk_end : unit_end_it;
+      kb_end = kb_begin + (int)(e - sk_cur);
+      tile = tile_of(unit);
+      split = 0;
+      role = kb_begin != 0 ? 1 : (e < unit_end_it ? 2 : 0);
+      sk_cur = e;
+      return true;
+    }
+    if (SK && next_unit < units) {
+      tile = tile_of(next_unit);
+      split = 0;
+      kb_begin = 0;
+      kb_end = num_kb;
+      role = 0;
+      next_unit += n_groups;
+      return true;
+    }
+    if (next_item < total_items) {
+      split = next_item % splits;
+      tile = next_item / splits;
+      kb_begin = split * kb_per_split;
+      kb_end = min(num_kb, kb_begin + kb_per_split);
+      role = 0;
+      next_item += (int)gridDim.x;
+      return true;
+    }
+    return false;
+  }
+  // number of following groups whose range starts inside the current unit (the owner's contributors)
+  SK_DEVINL int n_contrib() const {
+    int n = 0;
+    for (int g = grp + 1; g < sk_groups && sk_total * g / sk_groups < unit_end_it; ++g) ++n;
+    return n;
+  }
+};
+
+SK_DEVINL uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+SK_DEVINL void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// bias (+ activation) on 8 consecutive accumulator columns starting at `col`
+SK_DEVINL void epi_bias_act(float (&v)[8], const GemmParams& p, int col) {
+  if (p.bias) {
+    if (p.bias_f32) {
+      const float* bp = reinterpret_cast<const float*>(p.bias) + col;
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    } else {
+      const uint4 bv = ldg128(reinterpret_cast<const bf16*>(p.bias) + col);
+      const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16(bw[i]);
+        v[2 * i] += f.x;
+        v[2 * i + 1] += f.y;
+      }
+    }
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+  }
+}
+
+// residual (hi, and lo when present) read at output column `ocol` of row `row`
+SK_DEVINL void epi_residual(float (&v)[8], const GemmParams& p, size_t row, int ocol) {
+  if (!p.residual) return;
+  const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + ocol);
+  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_bf16(rw[i]);
+    if (p.round_before_res) {
+      v[2 * i] = bf16_round(v[2 * i]) + f.x;
+      v[2 * i + 1] = bf16_round(v[2 * i + 1]) + f.y;
+    } else {
+      v[2 * i] += f.x;
+      v[2 * i + 1] += f.y;
+    }
+  }
+  if (p.residual_lo) {
+    const uint4 lv = *reinterpret_cast<const uint4*>(p.residual_lo + row * p.ldr + ocol);
+    const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16(lw[i]);
+      v[2 * i] += f.x;
+      v[2 * i + 1] += f.y;
+    }
+  }
+}
+
+// Stream-K partial tiles live in p.sk_ws, one 128 x 256 fp32 slot per CTA, laid out [32-col chunk][float4 j][row][4]
+// so that a warp (32 consecutive rows) stores and loads 512 contiguous bytes per access.
+constexpr int SK_SLOT_FLOATS = BM * 256;
+SK_DEVINL size_t sk_slot_off(int chunk, int j4, int row_in_tile) { return ((size_t)(chunk * 8 + j4) * BM + row_in_tile) * 4; }
+
+// add the partial tiles of n following groups (CTA first_cta, first_cta + G, ...) to the 32 accumulator columns in r;
+// loads of two partials are in flight together, the additions keep the group order
+SK_DEVINL void sk_fixup_add(uint32_t (&r)[32], const float* ws, int chunk, int row_in_tile, int first_cta, int G, int n) {
+  for (int c0 = 0; c0 < n; c0 += 2) {
+    float4 a[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (c0 + u < n) {
+        const float* slot = ws + (size_t)(first_cta + (c0 + u) * G) * SK_SLOT_FLOATS;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[u][j] = __ldcg(reinterpret_cast<const float4*>(slot + sk_slot_off(chunk, j, row_in_tile)));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (c0 + u < n) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + a[u][j].x);
+          r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + a[u][j].y);
+          r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + a[u][j].z);
+          r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + a[u][j].w);
+        }
+      }
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, bool SK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo,
@@ -86,9 +285,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
-  const int num_tiles = tiles_per_batch * p.batch * p.splits;   // work items
+  const int total_items = tiles_per_batch * p.batch * p.splits;
   const int num_kb_total = (p.K + BK - 1) / BK;
   const int kb_per_split = (num_kb_total + p.splits - 1) / p.splits;
+  // bytes one stage receives: A tile + B tile (a K-major B box is exactly BN rows; MN-major B comes in 64-column atoms)
+  constexpr uint32_t STAGE_TX = Cfg::A_BYTES + (B_MN ? Cfg::B_ATOMS * 64 * BK * 2 : BN * BK * 2);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -117,25 +318,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int split = t % p.splits;
-        const int tt = t / p.splits;
-        const int bidx = tt / tiles_per_batch;
-        const int r = tt - bidx * tiles_per_batch;
+      WorkIter<SK> w(p, num_kb_total, kb_per_split, total_items);
+      while (w.next()) {
+        const int bidx = w.tile / tiles_per_batch;
+        const int r = w.tile - bidx * tiles_per_batch;
         const int m0 = (r / p.tiles_n) * BM;
         const int n_blk = r % p.tiles_n;
         const int n0 = n_blk * BN;
-        const int kb_begin = split * kb_per_split;
-        const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
         for (int pass = 0; pass < p.passes; ++pass) {
           const CUtensorMap* mapA = (pass == 2) ? &tmA_lo : &tmA;
           const CUtensorMap* mapB = (pass == 1) ? &tmB_lo : &tmB;
-          for (int kb = kb_begin; kb < kb_end; ++kb) {
+          for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sB = sA + Cfg::A_BYTES;
             const uint32_t fb = full_bar(stage);
-            mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+            mbar_arrive_expect_tx(fb, STAGE_TX);
             if (!A_MN) {
               if (p.a_mode & 2) {
                 if (p.a_mode & 1) tma_load_3d(sA, mapA, fb, n_blk * 64, m0 + kb, bidx);
@@ -151,7 +349,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_load_2d(sB, mapB, fb, kb * BK, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), mapB, fb, n0 + 64 * j, kb * BK);
+              for (int j = 0; j < Cfg::B_ATOMS; ++j) tma_load_2d(sB + j * (BK * 128), mapB, fb, n0 + 64 * j, kb * BK);
             }
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -166,14 +364,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      WorkIter<SK> w(p, num_kb_total, kb_per_split, total_items);
+      while (w.next()) {
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
-        const int split = t % p.splits;
-        const int kb_begin = split * kb_per_split;
-        const int kb_cnt = max(0, min(num_kb_total, kb_begin + kb_per_split) - kb_begin);
-        const int k_iters = kb_cnt * p.passes;
+        const int k_iters = max(0, w.kb_end - w.kb_begin) * p.passes;
         for (int kb = 0; kb < k_iters; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -201,188 +397,157 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     uint32_t store_cnt = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int split = t % p.splits;
-      const int tt = t / p.splits;
-      const int bidx = tt / tiles_per_batch;
-      const int rr = tt - bidx * tiles_per_batch;
+    WorkIter<SK> w(p, num_kb_total, kb_per_split, total_items);
+    while (w.next()) {
+      const int split = w.split;
+      const int bidx = w.tile / tiles_per_batch;
+      const int rr = w.tile - bidx * tiles_per_batch;
       const int m0 = (rr / p.tiles_n) * BM;
       const int n0 = (rr % p.tiles_n) * BN;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int row_in = m0 + q * 32 + lane;
+      const int row_in_tile = q * 32 + lane;
+      const int row_in = m0 + row_in_tile;
       const bool row_ok = row_in < p.M;
       const size_t row = (size_t)bidx * p.M + row_in;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * Cfg::ACC_STRIDE);
-      if (p.tma_store) {
-        // coalesced path: TMEM -> registers -> 128B-swizzled smem (this warp's private 32-row buffer) -> TMA store
+      const int first_contrib = (int)blockIdx.x + w.G;   // same member of the next group
+      const int n_contrib = (SK && w.role == 2) ? w.n_contrib() : 0;
+      if (SK && w.role == 1) {
+        // stream-K contributor: this quadrant's rows of the fp32 partial -> workspace slot, then publish
+        float* slot = p.sk_ws + (size_t)blockIdx.x * SK_SLOT_FLOATS;
 #pragma unroll 1
-        for (int c2 = 0; c2 < BN / 64; ++c2) {
-          const uint32_t sbuf = staging_base + (uint32_t)(warp - 2) * 8192u + (store_cnt & 1u) * 4096u;
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c2 * 64 + half * 32, r);
-            tmem_ld_wait();
+          for (int j = 0; j < 8; ++j)
+            __stcg(reinterpret_cast<float4*>(slot + sk_slot_off(c, j, row_in_tile)),
+                   make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3])));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u32(p.sk_flags + blockIdx.x * 4 + q, 1u);
+      } else {
+        if (SK && w.role == 2) {
+          // wait until every CTA that holds a later K range of this tile has published this quadrant's rows
+          if (lane == 0) {
+            for (int i = 0; i < n_contrib; ++i) {
+              const int c = first_contrib + i * w.G;
+              const uint32_t* f = p.sk_flags + c * 4 + q;
+              const uint64_t t0 = globaltimer_ns();
+              while (ld_acquire_u32(f) == 0u) {
+                __nanosleep(64);
+                if (globaltimer_ns() - t0 > 8000000000ull) {
+                  printf("slamkit_b200: stream-K flag wait timed out (cta %d waits for %d)\n", (int)blockIdx.x, c);
+                  __trap();
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+        if (p.tma_store) {
+          // coalesced path: TMEM -> registers -> 128B-swizzled smem (this warp's private 32-row buffer) -> TMA store
+#pragma unroll 1
+          for (int c2 = 0; c2 < BN / 64; ++c2) {
+            const uint32_t sbuf = staging_base + (uint32_t)(warp - 2) * 8192u + (store_cnt & 1u) * 4096u;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t r[32];
+              tmem_ld_32x32(taddr + c2 * 64 + half * 32, r);
+              tmem_ld_wait();
+              if (SK && n_contrib > 0) sk_fixup_add(r, p.sk_ws, c2 * 2 + half, row_in_tile, first_contrib, w.G, n_contrib);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = n0 + c2 * 64 + half * 32 + g * 8;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                if (col < p.N) {
+                  epi_bias_act(v, p, col);
+                  if (row_ok) epi_residual(v, p, row, col);
+                }
+                const int j = half * 4 + g;
+                const uint32_t dst = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16(v[0], v[1])),
+                             "r"(pack_bf16(v[2], v[3])), "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7]))
+                             : "memory");
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, sbuf, n0 + c2 * 64, m0 + q * 32);
+              tma_store_commit();
+            }
+            ++store_cnt;
+          }
+        }
+        else
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (SK && n_contrib > 0) sk_fixup_add(r, p.sk_ws, c, row_in_tile, first_contrib, w.G, n_contrib);
+          const int col0 = n0 + c * 32;
+          if (row_ok && col0 < p.N) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const int col = n0 + c2 * 64 + half * 32 + g * 8;
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+              const int col = col0 + g * 8;
               if (col < p.N) {
-                if (p.bias) {
-                  if (p.bias_f32) {
-                    const float* bp = reinterpret_cast<const float*>(p.bias) + col;
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
-                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                  } else {
-                    const uint4 bv = ldg128(reinterpret_cast<const bf16*>(p.bias) + col);
-                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                float v[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                      const float2 f = unpack_bf16(bw[i]);
-                      v[2 * i] += f.x;
-                      v[2 * i + 1] += f.y;
-                    }
-                  }
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                if (p.splits > 1) {
+                  float* dst = p.splitk_ws + ((size_t)split * p.M + row_in) * p.N + col;
+                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                  continue;
                 }
-                if (p.act == 1) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+                epi_bias_act(v, p, col);
+                int ocol = col;
+                if (p.col_gin > 0) {
+                  const int gi = col / p.col_gin, ci = col - gi * p.col_gin;
+                  if (ci >= p.col_gout) continue;
+                  ocol = gi * p.col_gout + ci;
                 }
-                if (p.residual && row_ok) {
-                  const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col);
-                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float2 f = unpack_bf16(rw[i]);
-                    if (p.round_before_res) {
-                      v[2 * i] = bf16_round(v[2 * i]) + f.x;
-                      v[2 * i + 1] = bf16_round(v[2 * i + 1]) + f.y;
-                    } else {
-                      v[2 * i] += f.x;
-                      v[2 * i + 1] += f.y;
-                    }
-                  }
-                }
-              }
-              const int j = half * 4 + g;
-              const uint32_t dst = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16(v[0], v[1])),
-                           "r"(pack_bf16(v[2], v[3])), "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7]))
-                           : "memory");
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, sbuf, n0 + c2 * 64, m0 + q * 32);
-            tma_store_commit();
-          }
-          ++store_cnt;
-        }
-      } else
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < p.N) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              if (p.splits > 1) {
-                float* dst = p.splitk_ws + ((size_t)split * p.M + row_in) * p.N + col;
-                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                continue;
-              }
-              if (p.bias) {
-                if (p.bias_f32) {
-                  const float* bp = reinterpret_cast<const float*>(p.bias) + col;
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                epi_residual(v, p, row, ocol);
+                if (p.out_f32) {
+                  float* dst = reinterpret_cast<float*>(p.C) + row * p.ldc + ocol;
+                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
                 } else {
-                  const uint4 bv = ldg128(reinterpret_cast<const bf16*>(p.bias) + col);
-                  const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float2 f = unpack_bf16(bw[i]);
-                    v[2 * i] += f.x;
-                    v[2 * i + 1] += f.y;
+                  uint4 o;
+                  o.x = pack_bf16(v[0], v[1]);
+                  o.y = pack_bf16(v[2], v[3]);
+                  o.z = pack_bf16(v[4], v[5]);
+                  o.w = pack_bf16(v[6], v[7]);
+                  stg128(reinterpret_cast<bf16*>(p.C) + row * p.ldc + ocol, o);
+                  if (p.C_lo) {
+                    const float2 h0 = unpack_bf16(o.x), h1 = unpack_bf16(o.y), h2 = unpack_bf16(o.z), h3 = unpack_bf16(o.w);
+                    uint4 l;
+                    l.x = pack_bf16(v[0] - h0.x, v[1] - h0.y);
+                    l.y = pack_bf16(v[2] - h1.x, v[3] - h1.y);
+                    l.z = pack_bf16(v[4] - h2.x, v[5] - h2.y);
+                    l.w = pack_bf16(v[6] - h3.x, v[7] - h3.y);
+                    stg128(reinterpret_cast<bf16*>(p.C_lo) + row * p.ldc + ocol, l);
                   }
-                }
-              }
-              if (p.act == 1) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
-              }
-              int ocol = col;
-              if (p.col_gin > 0) {
-                const int gi = col / p.col_gin, ci = col - gi * p.col_gin;
-                if (ci >= p.col_gout) continue;
-                ocol = gi * p.col_gout + ci;
-              }
-              if (p.residual) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + ocol);
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = unpack_bf16(rw[i]);
-                  if (p.round_before_res) {
-                    v[2 * i] = bf16_round(v[2 * i]) + f.x;
-                    v[2 * i + 1] = bf16_round(v[2 * i + 1]) + f.y;
-                  } else {
-                    v[2 * i] += f.x;
-                    v[2 * i + 1] += f.y;
-                  }
-                }
-                if (p.residual_lo) {
-                  const uint4 lv = *reinterpret_cast<const uint4*>(p.residual_lo + row * p.ldr + ocol);
-                  const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float2 f = unpack_bf16(lw[i]);
-                    v[2 * i] += f.x;
-                    v[2 * i + 1] += f.y;
-                  }
-                }
-              }
-              if (p.out_f32) {
-                float* dst = reinterpret_cast<float*>(p.C) + row * p.ldc + ocol;
-                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              } else {
-                uint4 o;
-                o.x = pack_bf16(v[0], v[1]);
-                o.y = pack_bf16(v[2], v[3]);
-                o.z = pack_bf16(v[4], v[5]);
-                o.w = pack_bf16(v[6], v[7]);
-                stg128(reinterpret_cast<bf16*>(p.C) + row * p.ldc + ocol, o);
-                if (p.C_lo) {
-                  const float2 h0 = unpack_bf16(o.x), h1 = unpack_bf16(o.y), h2 = unpack_bf16(o.z), h3 = unpack_bf16(o.w);
-                  uint4 l;
-                  l.x = pack_bf16(v[0] - h0.x, v[1] - h0.y);
-                  l.y = pack_bf16(v[2] - h1.x, v[3] - h1.y);
-                  l.z = pack_bf16(v[4] - h2.x, v[5] - h2.y);
-                  l.w = pack_bf16(v[6] - h3.x, v[7] - h3.y);
-                  stg128(reinterpret_cast<bf16*>(p.C_lo) + row * p.ldc + ocol, l);
                 }
               }
             }
           }
+        }
+        if (SK && w.role == 2) {
+          // partials consumed: re-arm the flags for the next launch that shares this workspace
+          __syncwarp();
+          if (lane == 0)
+            for (int i = 0; i < n_contrib; ++i) p.sk_flags[(first_contrib + i * w.G) * 4 + q] = 0u;
         }
       }
       tc_fence_before();
@@ -490,35 +655,40 @@ int sk_make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
 
 namespace {
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool SK>
 int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    SK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
   sk_prof_begin(0, stream);
-  gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  gemm_tcgen05_kernel<BN, A_MN, B_MN, SK><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
   sk_prof_end(stream);
   SK_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BN>
+template <int BN, bool SK>
 int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tm, p, grid, s);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tm, p, grid, s);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tm, p, grid, s);
-  return launch_gemm<BN, true, true>(tm, p, grid, s);
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, SK>(tm, p, grid, s);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, SK>(tm, p, grid, s);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, SK>(tm, p, grid, s);
+  return launch_gemm<BN, true, true, SK>(tm, p, grid, s);
 }
 
 // Relative cost of one 128 x BN tile (BN=256 == 100), measured on B200 (profiles/r01_gemm_bench.txt): narrow tiles
 // pay the per-tile pipeline fill / epilogue overhead and re-read the A tile from shared memory more often per FLOP.
+// (A 224-wide tile, which would fit N = 896 exactly, was measured no faster per tile than 256: r01_gemm_bench_v3.)
 inline int tile_cost(int bn) { return bn >= 256 ? 100 : (bn >= 128 ? 61 : 54); }
 
+constexpr size_t SK_FLAG_BYTES = 4096;   // tail of the scratch buffer: stream-K publish flags
+
 }  // namespace
+
+size_t sk_gemm_ws_min_bytes(void) { return (size_t)sk_num_sms() * SK_SLOT_FLOATS * sizeof(float) + SK_FLAG_BYTES; }
 
 int sk_pick_bn(int M, int N, int force_bn) {
   if (force_bn == 64 || force_bn == 128 || force_bn == 256) return force_bn;
@@ -552,6 +722,17 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
   const bool use3d = g.a_rows > 0;   // strided-window / batched A view
   SK_REQUIRE(!use3d || !g.a_mn, "gemm: a batched / windowed A operand must be K-major");
   SK_REQUIRE(g.a_mode == 0 || use3d, "gemm: a_mode 1 needs the 3-D A view");
+  const int nsm = sk_num_sms();
+  // stream-K needs the plain 2-D form and a scratch buffer of sk_gemm_ws_min_bytes() whose last 4 KB (flags) are zero
+  static const int sk_env = [] { const char* e = getenv("SK_STREAMK"); return e ? atoi(e) : 1; }();
+  // measured (profiles/r01_gemm_bench_v3_streamk.txt, A/B inside the LM step): balancing pays when whole-tile waves
+  // would leave >= ~20 % of the SM-time idle (gu_wgrad: 304 tiles = 2.05 waves, 144 -> 125 us); at 13 % idle the
+  // fix-up traffic eats the gain
+  static const int sk_min_idle = [] { const char* e = getenv("SK_STREAMK_MIN_IDLE"); return e ? atoi(e) : 20; }();
+  static const int sk_min_kb = [] { const char* e = getenv("SK_STREAMK_MIN_KB"); return e ? atoi(e) : 32; }();
+  const bool sk_ok = sk_env != 0 && g.batch == 1 && !use3d && g.passes == 1 && g.a_mode == 0 && g.splitk_ws != nullptr &&
+                     g.splitk_ws_bytes >= sk_gemm_ws_min_bytes();
+  const size_t ws_data_bytes = g.splitk_ws_bytes > SK_FLAG_BYTES ? g.splitk_ws_bytes - SK_FLAG_BYTES : 0;
   const int BN = (g.a_mode == 1) ? 64 : sk_pick_bn(g.M * g.batch, g.N, g.force_bn);
   CUtensorMap tm[5];
   const void* As[2] = {g.A, g.passes == 3 ? g.A_lo : g.A};
@@ -590,17 +771,16 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
   p.act = g.act;
   p.col_gin = g.col_gin; p.col_gout = g.col_gout;
   const long tiles = (long)p.tiles_m * p.tiles_n * g.batch;
-  const int nsm = sk_num_sms();
   // split-K: only for plain bf16-output GEMMs that leave most SMs idle and have a long K loop (the small wgrads)
   p.splits = 1;
   p.splitk_ws = nullptr;
   const int num_kb = (g.K + BK - 1) / BK;
   if (g.splitk_ws && g.batch == 1 && g.passes == 1 && !g.out_f32 && !g.bias && !g.act && !g.C_lo && g.col_gin == 0 &&
-      tiles * 2 <= nsm && num_kb >= 16) {
+      (g.residual == nullptr || g.residual == g.C) && tiles * 2 <= nsm && num_kb >= 16) {
     int sp = (int)(nsm / tiles);
     if (sp > 8) sp = 8;
     if (sp > num_kb / 4) sp = num_kb / 4;
-    if ((size_t)sp * g.M * g.N * sizeof(float) > g.splitk_ws_bytes) sp = (int)(g.splitk_ws_bytes / ((size_t)g.M * g.N * sizeof(float)));
+    if ((size_t)sp * g.M * g.N * sizeof(float) > ws_data_bytes) sp = (int)(ws_data_bytes / ((size_t)g.M * g.N * sizeof(float)));
     if (sp >= 2) {
       const int per = (num_kb + sp - 1) / sp;
       sp = (num_kb + per - 1) / per;   // no empty split: every work item issues at least one MMA
@@ -618,13 +798,44 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
     if (rc2) return rc2;
     p.tma_store = 1;
   }
+  // stream-K over the units (rows or columns of tiles) of the last, partial wave -- see WorkIter
+  p.sk_units = 0;
+  p.sk_groups = 0;
+  p.sk_G = 1;
+  p.sk_colunits = 0;
+  p.units = 0;
+  p.n_groups = 0;
+  p.sk_ws = nullptr;
+  p.sk_flags = nullptr;
+  if (sk_ok && BN == 256 && p.splits == 1 && num_kb >= sk_min_kb && (p.tiles_n <= 8 || (sk_env >= 2 && p.tiles_m <= 8))) {
+    const int colunits = p.tiles_n <= 8 ? 0 : 1;
+    const int G = colunits ? p.tiles_m : p.tiles_n;
+    const int units = colunits ? p.tiles_n : p.tiles_m;
+    const int n_groups = nsm / G;
+    const int rem = units % n_groups;
+    const long slots = ((long)(units + n_groups - 1) / n_groups) * n_groups;
+    if (n_groups >= 1 && rem != 0 && (slots - units) * 100 >= slots * sk_min_idle) {   // enough SM-time would idle
+      p.sk_units = rem;
+      p.sk_groups = n_groups < rem * 4 ? n_groups : rem * 4;            // a unit is cut into at most ~4 ranges
+      p.sk_G = G;
+      p.sk_colunits = colunits;
+      p.units = units;
+      p.n_groups = n_groups;
+      p.sk_ws = reinterpret_cast<float*>(g.splitk_ws);
+      p.sk_flags = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(g.splitk_ws) + ws_data_bytes);
+    }
+  }
   const long work = tiles * p.splits;
-  const int grid = (int)(work < nsm ? work : nsm);
+  const int grid = p.sk_units > 0 ? p.n_groups * p.sk_G : (int)(work < nsm ? work : nsm);
   int rc;
-  switch (BN) {
-    case 256: rc = dispatch_major<256>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
-    case 128: rc = dispatch_major<128>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
-    default:  rc = dispatch_major<64>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
+  if (p.sk_units > 0) {
+    rc = dispatch_major<256, true>(g.a_mn, g.b_mn, tm, p, grid, stream);
+  } else {
+    switch (BN) {
+      case 256: rc = dispatch_major<256, false>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
+      case 128: rc = dispatch_major<128, false>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
+      default:  rc = dispatch_major<64, false>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
+    }
   }
   if (rc) return rc;
   if (p.splits > 1) {

@@ -445,9 +445,21 @@ int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const 
   conv0_affine_kernel<<<g2, 128, 0, s>>>(stats, w, gamma, beta, affine, C, KW, T0, eps);
   SK_LAUNCH_CHECK();
   const int fpb = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
-  int gx = (T0 + fpb - 1) / fpb;
-  const int cap = std::max(1, sk_num_sms() * 4 / B);
-  if (gx > cap) gx = cap;
+  // grid (gx, B): a few CTAs per resident slot, gx chosen so that gx * B fills whole waves of resident CTAs
+  static int occ = 0;
+  if (occ == 0) {
+    SK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv0_apply_kernel<8>, 256, 0));
+    if (occ < 1) occ = 1;
+  }
+  const long slots = (long)sk_num_sms() * occ;
+  const int gx_max = std::max(1, std::min((T0 + fpb - 1) / fpb, (int)std::max(1L, slots * 8 / B)));
+  int gx = gx_max;
+  double best = -1.0;
+  for (int cand = gx_max; cand >= std::max(1, gx_max / 4); --cand) {
+    const long ctas = (long)cand * B;
+    const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
+    if (eff > best + 1e-9) { best = eff; gx = cand; }
+  }
   sk_prof_begin(3, s);
   conv0_apply_kernel<8><<<dim3(gx, B), 256, 0, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
   sk_prof_end(s);

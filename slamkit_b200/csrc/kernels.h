@@ -9,6 +9,7 @@ int sk_make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t 
 int sk_make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride,
                     uint64_t batch_stride, uint32_t box_rows);
 int sk_pick_bn(int M, int N, int force_bn);
+size_t sk_gemm_ws_min_bytes(void);   // scratch size that enables stream-K (last 4 KB = flag words, zero on first use)
 // Extended GEMM description (HuBERT path): batched / strided-window A operands (convolutions as GEMMs without an
 // im2col copy), split-bf16 3-pass accumulation, fp32 bias, hi/lo residual and outputs, grouped column compaction.
 struct SkGemmEx {
@@ -29,7 +30,7 @@ struct SkGemmEx {
   int ldr, round_before_res, act;
   int col_gin, col_gout;
   int force_bn;
-  void* splitk_ws;          // optional fp32 scratch enabling deterministic split-K for small-output / long-K GEMMs
+  void* splitk_ws;          // optional scratch: deterministic split-K (few tiles, long K) and stream-K load balancing
   size_t splitk_ws_bytes;
 };
 int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream);

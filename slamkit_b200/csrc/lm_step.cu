@@ -5,6 +5,7 @@
 // HF Trainer's inner step.  No tensor library is involved below the C ABI: raw device pointers in, kernels out.
 #include "kernels.h"
 #include "../../include/slamkit_b200.h"
+#include <algorithm>
 #include <string>
 #include <vector>
 #include <math.h>
@@ -85,6 +86,10 @@ WsLayout make_layout(const SkLm* lm, int B, int T) {
   w.slse = align_up((int64_t)B * lm->H * T * 4, 256);
   w.sgu = align_up(M * 2 * lm->F * 2, 256);
   w.sact = align_up(M * lm->F * 2, 256);
+  // GEMM scratch first: its offset (and the stream-K flag words in its last 4 KB, zeroed by sk_lm_bind) must not move
+  // with (B, T).  Sized for 8 fp32 slabs of the largest split-K wgrad and for the stream-K partial tiles.
+  w.splitk_bytes = align_up(std::max<int64_t>((int64_t)8 * lm->qkv_dim * lm->d * 4, (int64_t)sk_gemm_ws_min_bytes()) + 4096, 256);
+  w.splitk = take(w.splitk_bytes);
   w.X = take(w.sX * (L + 1));
   w.h1 = take(w.sh * L);
   w.rstd1 = take(w.srstd * L);
@@ -112,8 +117,6 @@ WsLayout make_layout(const SkLm* lm, int B, int T) {
   w.colsum_partial = take((int64_t)sk_colsum_splits() * lm->qkv_dim * 4);
   w.ce_partial = take((int64_t)sk_ce_blocks((int)M) * 2 * 4);
   w.embed_scratch = take((int64_t)lm->Vp * lm->d * 4);
-  w.splitk_bytes = (int64_t)8 * lm->qkv_dim * lm->d * 4;   // up to 8 fp32 slabs of the largest split-K wgrad
-  w.splitk = take(w.splitk_bytes);
   w.attn_partial = take((int64_t)B * lm->H * T * 128 * 4);   // per-head fp32 dK|dV partials (tcgen05 backward)
   w.total = cur;
   return w;
@@ -131,6 +134,8 @@ T* wsp(const SkLm* lm, int64_t off) {
   } while (0)
 
 // y[M,N] = x[M,K] * W[N,K]^T (+bias) (+residual)
+// (forward and dgrad GEMMs get no scratch: whole-tile scheduling keeps every output row's fp32 summation order
+//  independent of the batch it sits in -- logits of a sequence are bit-identical alone or inside a batch)
 int linear_fwd(int M, int N, int K, const bf16* x, const bf16* W, bf16* y, const bf16* bias, const bf16* res,
                cudaStream_t s) {
   return sk_gemm_launch(M, N, K, x, K, 0, W, K, 0, y, N, 0, bias, res, N, res ? 1 : 0, 0, 0, s);
@@ -139,7 +144,7 @@ int linear_fwd(int M, int N, int K, const bf16* x, const bf16* W, bf16* y, const
 int linear_dgrad(int M, int N, int K, const bf16* dy, const bf16* W, bf16* dx, cudaStream_t s) {
   return sk_gemm_launch(M, K, N, dy, N, 0, W, K, 1, dx, K, 0, nullptr, nullptr, 0, 0, 0, 0, s);
 }
-// dW[N,K] (+)= dy[M,N]^T * x[M,K]
+// dW[N,K] (+)= dy[M,N]^T * x[M,K]   (scratch: split-K for the small wgrads, stream-K balancing for the large ones)
 int linear_wgrad(int M, int N, int K, const bf16* dy, const bf16* x, bf16* dW, int accumulate, cudaStream_t s,
                  void* splitk_ws, size_t splitk_bytes) {
   return sk_gemm_launch(N, K, M, dy, N, 1, x, K, 1, dW, K, 0, nullptr, accumulate ? dW : nullptr, K, 1, 0, 0, s,
@@ -382,6 +387,12 @@ int sk_lm_bind(SkLm* lm, void* params, void* grads, const void* rope_cos, const 
   lm->rope_sin = reinterpret_cast<const bf16*>(rope_sin);
   lm->ws = reinterpret_cast<uint8_t*>(workspace);
   lm->ws_bytes = workspace_bytes;
+  // stream-K publish flags (last 4 KB of the GEMM scratch, which sits at a fixed offset) start out zero; the GEMM
+  // re-arms them itself after every launch
+  const WsLayout w = make_layout(lm, 1, 1);
+  SK_REQUIRE(workspace_bytes >= w.splitk + w.splitk_bytes, "sk_lm_bind: workspace smaller than the GEMM scratch");
+  SK_CUDA_CHECK(cudaMemset(lm->ws + w.splitk + w.splitk_bytes - 4096, 0, 4096));
+  SK_CUDA_CHECK(cudaDeviceSynchronize());
   return 0;
 }
 

@@ -19,11 +19,24 @@ def _bf16(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+_gemm_ws = {}
+
+
+def gemm_workspace(device) -> torch.Tensor:
+    """Per-device GEMM scratch (stream-K partial tiles + flag words; zeroed once, re-armed by the kernel)."""
+    lib = L.require_cuda()
+    key = torch.device(device).index or 0
+    if key not in _gemm_ws:
+        _gemm_ws[key] = torch.zeros(int(lib.sk_gemm_ws_bytes()) + (64 << 20), dtype=torch.uint8, device=device)
+    return _gemm_ws[key]
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
          bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          out: Optional[torch.Tensor] = None, out_f32: bool = False, round_before_res: bool = False,
-         act: int = 0, force_bn: int = 0) -> torch.Tensor:
-    """C = A @ B^T (+bias) (+residual).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn)."""
+         act: int = 0, force_bn: int = 0, streamk: bool = False) -> torch.Tensor:
+    """C = A @ B^T (+bias) (+residual).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn).
+    streamk=True hands the kernel the per-device scratch (sk_gemm_bf16_ws: stream-K balancing, 224-wide tiles)."""
     lib = L.require_cuda()
     _bf16(a), _bf16(b)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
@@ -33,6 +46,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     assert out.stride(1) == 1
+    if streamk:
+        ws = gemm_workspace(a.device)
+        L.check(lib.sk_gemm_bf16_ws(M, N, K, L.ptr(a), a.stride(0), int(a_mn), L.ptr(b), b.stride(0), int(b_mn),
+                                    L.ptr(out), out.stride(0), int(out_f32), L.ptr(bias), L.ptr(residual),
+                                    residual.stride(0) if residual is not None else 0, int(round_before_res), act,
+                                    force_bn, L.ptr(ws), C.c_int64(ws.numel()), L.stream_ptr()))
+        return out
     L.check(lib.sk_gemm_bf16(M, N, K, L.ptr(a), a.stride(0), int(a_mn), L.ptr(b), b.stride(0), int(b_mn), L.ptr(out),
                              out.stride(0), int(out_f32), L.ptr(bias), L.ptr(residual),
                              residual.stride(0) if residual is not None else 0, int(round_before_res), act, force_bn,
@@ -46,7 +66,7 @@ def gemm_splitk(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn: bo
     lib = L.require_cuda()
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N = b.shape[1] if b_mn else b.shape[0]
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=a.device)
     L.check(lib.sk_gemm_bf16_splitk(M, N, K, L.ptr(a), a.stride(0), int(a_mn), L.ptr(b), b.stride(0), int(b_mn), L.ptr(out),
                                     out.stride(0), int(accumulate), L.ptr(ws), C.c_int64(ws_bytes), L.stream_ptr()))
     return out

@@ -85,6 +85,49 @@ def test_gemm_splitk_wgrad(M, N, K, acc):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K,bn", [(2048, 896, 2048, 0), (4224, 1152, 2048, 0), (2560, 896, 4096, 256),
+                                       (2000, 1000, 2304, 256), (640, 4864, 2048, 256), (2048, 896, 2048, 128),
+                                       (1152, 896, 4096, 0), (9728, 896, 2048, 0)])
+def test_gemm_streamk(M, N, K, bn, a_mn, b_mn):
+    """Stream-K balancing (sk_gemm_bf16_ws): partial tiles meet in the scratch, fixed-order fix-up -> same result every
+    launch; all four operand layouts, ragged M / N edges, many and few contributors per tile."""
+    from slamkit_b200 import ops
+    a, b = _randn(M, K, seed=21), _randn(N, K, seed=22)
+    ref = a.float() @ b.float().t()
+    a_dev = a.t().contiguous().to(DEV) if a_mn else a.to(DEV)
+    b_dev = b.t().contiguous().to(DEV) if b_mn else b.to(DEV)
+    out = ops.gemm(a_dev, b_dev, a_mn=a_mn, b_mn=b_mn, force_bn=bn, streamk=True)
+    assert rel_err(out.cpu(), ref) < 4e-3, (M, N, K, bn, rel_err(out.cpu(), ref))
+    for _ in range(3):   # flags re-armed by the kernel; bit-identical
+        out2 = ops.gemm(a_dev, b_dev, a_mn=a_mn, b_mn=b_mn, force_bn=bn, streamk=True)
+        assert torch.equal(out, out2)
+    assert int(ops.gemm_workspace(DEV)[-4096:].max()) == 0
+
+
+def test_gemm_streamk_epilogues():
+    from slamkit_b200 import ops
+    M, N, K = 2048, 896, 2048
+    a, b = _randn(M, K, seed=5), _randn(N, K, seed=6)
+    bias, res = _randn(N, seed=7), _randn(M, N, seed=8)
+    acc = a.float() @ b.float().t()
+    ad, bd = a.to(DEV), b.to(DEV)
+    out = ops.gemm(ad, bd, bias=bias.to(DEV), residual=res.to(DEV), round_before_res=True, streamk=True).cpu()
+    ref = ((acc + bias.float()).to(torch.bfloat16).float() + res.float())
+    assert rel_err(out, ref) < 4e-3
+    out = ops.gemm(ad, bd, out_f32=True, streamk=True).cpu()
+    assert out.dtype == torch.float32 and rel_err(out, acc) < 1e-5
+    out = ops.gemm(ad, bd, bias=bias.to(DEV), act=1, streamk=True).cpu()
+    assert rel_err(out, torch.nn.functional.gelu(acc + bias.float())) < 4e-3
+    c = res.clone().to(DEV)
+    ops.gemm(ad, bd, residual=c, out=c, round_before_res=True, streamk=True)
+    assert rel_err(c.cpu(), acc.to(torch.bfloat16).float() + res.float()) < 4e-3
+    # same values as the plain launch up to fp32 summation order
+    plain = ops.gemm(ad, bd).float()
+    sk = ops.gemm(ad, bd, streamk=True).float()
+    assert rel_err(sk.cpu(), plain.cpu()) < 2e-3
+
+
 def test_gemm_rejects_bad_arguments():
     from slamkit_b200 import ops, _lib
     a, b = _randn(64, 64).to(DEV), _randn(60, 64).to(DEV)  # N=60 is not a multiple of 8

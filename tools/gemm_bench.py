@@ -29,6 +29,8 @@ shapes = [  # (name, M, N, K, a_mn, b_mn)
     ("down_fwd", M, 896, 4864, 0, 0), ("head_fwd", M, 512, 896, 0, 0),
     ("gu_dgrad", M, 896, 9728, 0, 1), ("down_dgrad", M, 4864, 896, 0, 1),
     ("gu_wgrad", 9728, 896, M, 1, 1), ("down_wgrad", 896, 4864, M, 1, 1), ("qkv_wgrad", 1152, 896, M, 1, 1),
+    ("qkv_dgrad", M, 896, 1152, 0, 1), ("o_dgrad", M, 896, 896, 0, 1), ("o_wgrad", 896, 896, M, 1, 1),
+    ("head_dgrad", M, 896, 512, 0, 1), ("head_wgrad", 512, 896, M, 1, 1),
 ]
 for name, m, n, k, a_mn, b_mn in shapes:
     a = torch.randn((k, m) if a_mn else (m, k), device=dev).to(torch.bfloat16)
@@ -36,9 +38,12 @@ for name, m, n, k, a_mn, b_mn in shapes:
     out = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
     flops = 2.0 * m * n * k
     res = []
-    for bn in (0, 64, 128, 256):
+    for bn in (0, 128, 256):
         t = timeit(lambda: ops.gemm(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), out=out, force_bn=bn))
         res.append(f"bn{bn}: {flops / t / 1e9:7.1f} TF/s ({t * 1e3:7.1f} us)")
+    for bn in (0,):   # with the scratch buffer: stream-K balancing
+        t = timeit(lambda: ops.gemm(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), out=out, force_bn=bn, streamk=True))
+        res.append(f"sk{bn}: {flops / t / 1e9:7.1f} TF/s ({t * 1e3:7.1f} us)")
     A = a.t() if a_mn else a
     Bt = b if b_mn else b.t()
     t = timeit(lambda: torch.matmul(A, Bt, out=out))
