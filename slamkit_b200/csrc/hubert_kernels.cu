@@ -9,26 +9,29 @@
 // kernels here read hi+lo, compute in fp32, and write hi/lo again.
 #include "kernels.h"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
 SK_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-// Branch-free erf for the conv0 front, where GELU runs on 3.1e9 elements per batch and libdevice's two-branch erff makes
-// the kernel instruction-bound: Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 absolute (below the 2^-17 relative
-// quantisation of the hi/lo output it feeds), 2 MUFU + 9 FP32 instructions.
-SK_DEVINL float erf_fast(float x) {
-  const float ax = fabsf(x);
+// Branch-free GELU(erf) for the conv0 front, where it runs on 3.1e9 elements per batch and the kernel is bound by
+// instruction issue, not by HBM (profiles/r01_ncu_conv0_apply_v2.txt).  erf from Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7 absolute, below the 2^-17 relative quantisation of the hi/lo output it feeds), folded into the GELU:
+//   gelu(y) = y/2 (1 + erf(y/sqrt2)),  erf|z| = 1 - P(t) exp(-z^2),  t = 1/(1 + p|z|)
+//           = relu(y) - |y| * (P(t)/2) * exp(-y^2/2)
+// -> 2 MUFU + 10 FMA-pipe + 1 ALU instruction, no sign fix-up, no separate 0.5x(1+erf) tail.
+SK_DEVINL float gelu_fast(float y) {
+  const float a = fabsf(y);
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(-ax * ax * 1.4426950408889634f);
-  return copysignf(fmaf(-p, e, 1.0f), x);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, a, 1.0f)));
+  float s = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  s = fmaf(s, t, 0.5f * 1.421413741f);
+  s = fmaf(s, t, 0.5f * -0.284496736f);
+  s = fmaf(s, t, 0.5f * 0.254829592f);
+  const float e = ex2_approx((y * y) * -0.72134752044448170368f);   // exp(-y^2/2)
+  const float q = (s * t) * e;
+  return fmaf(-a, q, fmaxf(y, 0.0f));
 }
-SK_DEVINL float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 SK_DEVINL void split_store(bf16* hi, bf16* lo, size_t idx, float v) {
   const bf16 h = __float2bfloat16_rn(v);
   hi[idx] = h;
@@ -38,8 +41,9 @@ SK_DEVINL void split8(const float (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float h0 = bf16_round(v[2 * k]), h1 = bf16_round(v[2 * k + 1]);
-    h[k] = pack_bf16(h0, h1);
+    // one packed convert for the hi pair, two integer ops to widen it back, one packed convert for the lo pair
+    h[k] = pack_bf16(v[2 * k], v[2 * k + 1]);
+    const float h0 = __uint_as_float(h[k] << 16), h1 = __uint_as_float(h[k] & 0xffff0000u);
     l[k] = pack_bf16(v[2 * k] - h0, v[2 * k + 1] - h1);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
@@ -157,10 +161,87 @@ __global__ void conv0_affine_kernel(const double* __restrict__ stats, const floa
 // channels (their CPT x KW taps and affine pairs live in registers for the whole kernel) and walks over frames; a warp
 // covers 32*CPT consecutive channels of one frame (coalesced 8- or 16-byte stores per thread).  No shared memory.
 // CPT = 4 keeps the kernel under 85 registers -> 3 CTAs (24 warps) per SM, which is what hides the MUFU / FMA chains.
-template <int CPT>
-__global__ void __launch_bounds__(256, CPT == 4 ? 3 : 2)
+// F2 = true pairs adjacent channels in packed fp32 registers so the 10 conv taps issue as 5 FFMA2 per channel pair
+// (same fp32 FMA chain per channel, half the issue slots; FFMA2 has no higher FLOP rate than FFMA on sm_100a --
+// profiles/r01_micro_ffma_vs_ffma2.txt -- the gain is issue bandwidth).
+typedef unsigned long long f32x2;
+SK_DEVINL f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+SK_DEVINL void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+SK_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+SK_DEVINL f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+SK_DEVINL f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+SK_DEVINL f32x2 dup2(float c) { return pk2(c, c); }
+// gelu_fast on NP packed pairs, written stage by stage so that the NP dependency chains (rcp -> 4 FMAs -> 2 muls ->
+// FMA, with a parallel mul -> mul -> ex2) interleave in the instruction stream: 10 packed FMA-pipe instructions, 4 MUFU,
+// 4 ALU per pair.  na = -|y| comes from OR-ing the sign bit, so t = 1 + p|y| = fma(-p, na, 1) and the tail is fma(na, q, relu(y)).
+template <int NP>
+SK_DEVINL void gelu_fast_pairs(f32x2 (&y)[NP]) {
+  f32x2 na[NP], t[NP], e[NP], s[NP], r[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float y0, y1;
+    upk2(y[i], y0, y1);
+    na[i] = pk2(__uint_as_float(__float_as_uint(y0) | 0x80000000u), __uint_as_float(__float_as_uint(y1) | 0x80000000u));
+    r[i] = pk2(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f));
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) t[i] = fma2(dup2(-0.3275911f * 0.70710678118654752440f), na[i], dup2(1.0f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) e[i] = mul2(mul2(y[i], y[i]), dup2(-0.72134752044448170368f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float a0, a1;
+    upk2(t[i], a0, a1);
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"(a0));
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"(a1));
+    t[i] = pk2(a0, a1);
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float a0, a1;
+    upk2(e[i], a0, a1);
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"(a0));
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"(a1));
+    e[i] = pk2(a0, a1);
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) s[i] = fma2(dup2(0.5f * 1.061405429f), t[i], dup2(0.5f * -1.453152027f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) s[i] = fma2(s[i], t[i], dup2(0.5f * 1.421413741f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) s[i] = fma2(s[i], t[i], dup2(0.5f * -0.284496736f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) s[i] = fma2(s[i], t[i], dup2(0.5f * 0.254829592f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) e[i] = mul2(e[i], t[i]);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) s[i] = mul2(s[i], e[i]);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) y[i] = fma2(na[i], s[i], r[i]);
+}
+
+template <int CPT, bool F2>
+__global__ void __launch_bounds__(256, 2)
 conv0_apply_kernel(const float* __restrict__ wav, const float* __restrict__ w, const float2* __restrict__ affine,
                    bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int S, int pad, int T0, int C, int KW, int ST) {
+  static_assert(CPT == 8, "conv0_apply: 8 channels per thread");
   const int b = blockIdx.y;
   const int groups = C / CPT;                     // channel groups per frame
   const int lanes_t = blockDim.x / groups > 0 ? blockDim.x / groups : 1;   // frames processed concurrently by a block
@@ -168,14 +249,27 @@ conv0_apply_kernel(const float* __restrict__ wav, const float* __restrict__ w, c
   const int tf = threadIdx.x / groups;
   if (tf >= lanes_t) return;
   // GroupNorm's per-(clip, channel) scale is folded into the taps, its shift seeds the accumulator
-  float wr[CPT][KW_MAX];
+  float wr[F2 ? 1 : CPT][KW_MAX];
+  f32x2 wr2[F2 ? CPT / 2 : 1][KW_MAX];
   float sh[CPT];
 #pragma unroll
-  for (int k = 0; k < CPT; ++k) {
-    const float2 a = affine[(size_t)b * C + cg * CPT + k];
-    sh[k] = a.y;
+  for (int k = 0; k < CPT; ++k) sh[k] = affine[(size_t)b * C + cg * CPT + k].y;
+  if (F2) {
 #pragma unroll
-    for (int j = 0; j < KW_MAX; ++j) wr[k][j] = j < KW ? __ldg(w + (cg * CPT + k) * KW + j) * a.x : 0.f;
+    for (int k = 0; k < CPT / 2; ++k) {
+      const float a0 = affine[(size_t)b * C + cg * CPT + 2 * k].x, a1 = affine[(size_t)b * C + cg * CPT + 2 * k + 1].x;
+#pragma unroll
+      for (int j = 0; j < KW_MAX; ++j)
+        wr2[k][j] = pk2(j < KW ? __ldg(w + (cg * CPT + 2 * k) * KW + j) * a0 : 0.f,
+                        j < KW ? __ldg(w + (cg * CPT + 2 * k + 1) * KW + j) * a1 : 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const float ax = affine[(size_t)b * C + cg * CPT + k].x;
+#pragma unroll
+      for (int j = 0; j < KW_MAX; ++j) wr[k][j] = j < KW ? __ldg(w + (cg * CPT + k) * KW + j) * ax : 0.f;
+    }
   }
   const float* wv = wav + (size_t)b * S;
   auto load_x = [&](int t, float (&x)[KW_MAX]) {
@@ -198,33 +292,161 @@ conv0_apply_kernel(const float* __restrict__ wav, const float* __restrict__ w, c
     for (int j = 0; j < KW_MAX; ++j) x[j] = xn[j];
     if (t + t_step < T0) load_x(t + t_step, xn);   // prefetch the next frame's window: hides the global-load latency
     float v[CPT];
+    if (F2) {
+      f32x2 y2[CPT / 2];
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-      float y = sh[k];
+      for (int k = 0; k < CPT / 2; ++k) y2[k] = pk2(sh[2 * k], sh[2 * k + 1]);
 #pragma unroll
-      for (int j = 0; j < KW_MAX; ++j) y = fmaf(wr[k][j], x[j], y);
-      v[k] = gelu_fast(y);
-    }
-    const size_t idx = ((size_t)b * T0 + t) * C + cg * CPT;
-    if (CPT == 8) {
-      float v8[8];
+      for (int j = 0; j < KW_MAX; ++j) {
+        const f32x2 xp = pk2(x[j], x[j]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v8[k] = v[k % CPT];
-      uint4 hi, lo;
-      split8(v8, hi, lo);
-      stg128(out_hi + idx, hi);
-      stg128(out_lo + idx, lo);
-    } else {
-      uint32_t h[CPT / 2], l[CPT / 2];
+        for (int k = 0; k < CPT / 2; ++k) y2[k] = fma2(wr2[k][j], xp, y2[k]);
+      }
 #pragma unroll
       for (int k = 0; k < CPT / 2; ++k) {
-        const float h0 = bf16_round(v[2 * k]), h1 = bf16_round(v[2 * k + 1]);
-        h[k] = pack_bf16(h0, h1);
-        l[k] = pack_bf16(v[2 * k] - h0, v[2 * k + 1] - h1);
+        float y0, y1;
+        upk2(y2[k], y0, y1);
+        v[2 * k] = gelu_fast(y0);
+        v[2 * k + 1] = gelu_fast(y1);
       }
-      *reinterpret_cast<uint2*>(out_hi + idx) = make_uint2(h[0], h[1]);
-      *reinterpret_cast<uint2*>(out_lo + idx) = make_uint2(l[0], l[1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        float y = sh[k];
+#pragma unroll
+        for (int j = 0; j < KW_MAX; ++j) y = fmaf(wr[k][j], x[j], y);
+        v[k] = gelu_fast(y);
+      }
     }
+    const size_t idx = ((size_t)b * T0 + t) * C + cg * CPT;
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    stg128(out_hi + idx, hi);
+    stg128(out_lo + idx, lo);
+  }
+}
+
+// Fast path for the HuBERT geometry (kernel 10, stride 5).
+//  * A thread owns 4 channels (2 packed pairs: 40 tap registers) and computes them for TWO consecutive frames per
+//    iteration; the frames' windows overlap, so 15 samples feed both (8 outputs per thread-iteration).
+//  * The waveform is staged through shared memory in chunks of CONV0_PCH frame pairs (coalesced loads, next chunk
+//    fetched into registers while the current one is computed).  With per-iteration global loads the loop was bound by
+//    the loaded HBM read latency (~0.9 us per iteration while 2.7 TB/s of stores are in flight: one load -> use
+//    dependency per iteration, 16 warps per SM) no matter how the arithmetic was arranged
+//    (profiles/r01_conv0_apply_experiments.txt).
+//  * GELU runs on packed pairs, stage by stage (gelu_fast_pairs), so the four dependency chains interleave and the
+//    FMA-pipe instruction count of the activation halves.
+constexpr int CONV0_PCH = 256;                       // frame pairs per chunk
+constexpr int CONV0_NS = 10 * CONV0_PCH + 8;         // samples per chunk (15 for the last pair, read as 8 float2; even)
+constexpr int CONV0_NLD = (CONV0_NS + 255) / 256;    // staged loads per thread per chunk
+__global__ void __launch_bounds__(256, 2)
+conv0_apply_k10s5_kernel(const float* __restrict__ wav, const float* __restrict__ w, const float2* __restrict__ affine,
+                         bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int S, int pad, int T0, int C) {
+  constexpr int KW = 10, ST = 5, NX = 16, CPT = 4;
+  __shared__ __align__(16) float sx[2][CONV0_NS];
+  const int b = blockIdx.y;
+  const int groups = C / CPT;                                             // channel groups per frame
+  const int rows = blockDim.x / groups > 0 ? blockDim.x / groups : 1;     // frame pairs a block works on concurrently
+  const int cg = threadIdx.x % groups;
+  const int tr = threadIdx.x / groups;
+  const bool active = tr < rows;
+  f32x2 wr2[CPT / 2][KW];
+  f32x2 sh2[CPT / 2];
+#pragma unroll
+  for (int k = 0; k < CPT / 2; ++k) {
+    const float2 a0 = affine[(size_t)b * C + cg * CPT + 2 * k], a1 = affine[(size_t)b * C + cg * CPT + 2 * k + 1];
+    sh2[k] = pk2(a0.y, a1.y);
+#pragma unroll
+    for (int j = 0; j < KW; ++j)
+      wr2[k][j] = pk2(__ldg(w + (cg * CPT + 2 * k) * KW + j) * a0.x, __ldg(w + (cg * CPT + 2 * k + 1) * KW + j) * a1.x);
+  }
+  const float* wv = wav + (size_t)b * S;
+  const int n_pairs = (T0 + 1) / 2;
+  const int n_chunks = (n_pairs + CONV0_PCH - 1) / CONV0_PCH;
+  float stage[CONV0_NLD];
+  auto fetch = [&](int chunk) {      // samples [10 * PCH * chunk - pad, +NS) of the clip, zero outside [0, S)
+    const long base = (long)2 * ST * CONV0_PCH * chunk - pad;
+#pragma unroll
+    for (int i = 0; i < CONV0_NLD; ++i) {
+      const long g = base + threadIdx.x + 256 * i;
+      stage[i] = (g >= 0 && g < S) ? __ldg(wv + g) : 0.f;
+    }
+  };
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < CONV0_NLD; ++i) {
+      const int o = threadIdx.x + 256 * i;
+      if (o < CONV0_NS) sx[buf][o] = stage[i];
+    }
+  };
+  int chunk = blockIdx.x;
+  int cur = 0;
+  if (chunk < n_chunks) {
+    fetch(chunk);
+    commit(0);
+  }
+  __syncthreads();
+  for (; chunk < n_chunks; chunk += gridDim.x) {
+    const bool more = chunk + (int)gridDim.x < n_chunks;
+    if (more) fetch(chunk + gridDim.x);            // in flight while this chunk is computed
+    if (active) {
+      const int p_end = min(CONV0_PCH, n_pairs - chunk * CONV0_PCH);
+      // running output pointers (frame 2*pr of this row; the odd frame is C elements further)
+      size_t idx = ((size_t)b * T0 + 2 * ((size_t)chunk * CONV0_PCH + tr)) * C + cg * CPT;
+      const size_t idx_step = (size_t)2 * rows * C;
+      for (int pp = tr; pp < p_end; pp += rows, idx += idx_step) {
+        float x[NX];
+        const float2* sp = reinterpret_cast<const float2*>(&sx[cur][2 * ST * pp]);   // 40 * pp bytes: 8-byte aligned
+#pragma unroll
+        for (int j = 0; j < NX / 2; ++j) {
+          const float2 t2 = sp[j];
+          x[2 * j] = t2.x;
+          x[2 * j + 1] = t2.y;
+        }
+        f32x2 y2[2][CPT / 2];
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int k = 0; k < CPT / 2; ++k) y2[f][k] = sh2[k];
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            const f32x2 xp = pk2(x[ST * f + j], x[ST * f + j]);
+#pragma unroll
+            for (int k = 0; k < CPT / 2; ++k) y2[f][k] = fma2(wr2[k][j], xp, y2[f][k]);
+          }
+        }
+        f32x2 gp[CPT];                    // 2 frames x 2 channel pairs
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int k = 0; k < CPT / 2; ++k) gp[f * (CPT / 2) + k] = y2[f][k];
+        gelu_fast_pairs<CPT>(gp);
+        const int pr = chunk * CONV0_PCH + pp;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const int t = 2 * pr + f;
+          if (t < T0) {
+            uint32_t h[2], l[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              float g0, g1, l0, l1;
+              upk2(gp[f * 2 + k], g0, g1);
+              h[k] = pack_bf16(g0, g1);
+              upk2(sub2(gp[f * 2 + k], pk2(__uint_as_float(h[k] << 16), __uint_as_float(h[k] & 0xffff0000u))), l0, l1);
+              l[k] = pack_bf16(l0, l1);
+            }
+            // streaming stores: 12.6 GB per batch must not push the waveform (and the next layer's weights) out of L2
+            __stcs(reinterpret_cast<uint2*>(out_hi + idx + (size_t)f * C), make_uint2(h[0], h[1]));
+            __stcs(reinterpret_cast<uint2*>(out_lo + idx + (size_t)f * C), make_uint2(l[0], l[1]));
+          }
+        }
+      }
+    }
+    if (more) commit(cur ^ 1);
+    __syncthreads();
+    cur ^= 1;
   }
 }
 
@@ -444,14 +666,18 @@ int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const 
   dim3 g2((C + 127) / 128, B);
   conv0_affine_kernel<<<g2, 128, 0, s>>>(stats, w, gamma, beta, affine, C, KW, T0, eps);
   SK_LAUNCH_CHECK();
-  const int fpb = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
+  // fast path: HuBERT's kernel 10 / stride 5 front with 4 channels x 2 frames per thread; generic kernel otherwise
+  static const int mode = [] { const char* e = getenv("SK_CONV0_MODE"); return e ? atoi(e) : 2; }();
+  const bool fast = mode == 2 && KW == 10 && ST == 5 && C % 4 == 0 && C / 4 <= 256;
+  const int fpb = fast ? 2 * CONV0_PCH : std::max(1, 256 / (C / 8));   // frames per block-iteration (fast: per chunk)
   // grid (gx, B): a few CTAs per resident slot, gx chosen so that gx * B fills whole waves of resident CTAs
-  static int occ = 0;
-  if (occ == 0) {
-    SK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv0_apply_kernel<8>, 256, 0));
-    if (occ < 1) occ = 1;
+  static int occ[2] = {0, 0};
+  if (occ[fast] == 0) {
+    if (fast) SK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], conv0_apply_k10s5_kernel, 256, 0));
+    else      SK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], conv0_apply_kernel<8, true>, 256, 0));
+    if (occ[fast] < 1) occ[fast] = 1;
   }
-  const long slots = (long)sk_num_sms() * occ;
+  const long slots = (long)sk_num_sms() * occ[fast];
   const int gx_max = std::max(1, std::min((T0 + fpb - 1) / fpb, (int)std::max(1L, slots * 8 / B)));
   int gx = gx_max;
   double best = -1.0;
@@ -461,7 +687,9 @@ int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const 
     if (eff > best + 1e-9) { best = eff; gx = cand; }
   }
   sk_prof_begin(3, s);
-  conv0_apply_kernel<8><<<dim3(gx, B), 256, 0, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
+  if (fast) conv0_apply_k10s5_kernel<<<dim3(gx, B), 256, 0, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C);
+  else if (mode == 1) conv0_apply_kernel<8, true><<<dim3(gx, B), 256, 0, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
+  else conv0_apply_kernel<8, false><<<dim3(gx, B), 256, 0, s>>>(wav, w, affine, out_hi, out_lo, S, pad, T0, C, KW, ST);
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;

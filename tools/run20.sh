@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_hubert.py tests/test_gpu_cli.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
+grep -E "passed|failed" gpurun_out/pytest_gpu.log | tail -2; grep -E "^FAILED|^ERROR|^E  " gpurun_out/pytest_gpu.log | cut -c1-300 | head -10
+for m in 0 2 0 2; do echo "SK_CONV0_MODE=$m"; SK_CONV0_MODE=$m timeout 600 python tools/hubert_time.py > gpurun_out/hubert_time_$m.json 2> gpurun_out/hubert_time.err; python - <<PY
+import json
+s = json.load(open("gpurun_out/hubert_time_$m.json"))
+print("HUBERT", round(s["value"],3), round(s["ms_per_batch"],2), round(s["roofline"]["achieved"],1), round(s["roofline"]["frac"],4), s["roofline"]["breakdown_ms"])
+PY
+done
