@@ -56,8 +56,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (T + AT_BR - 1) / AT_BR;
-  const int qt = n_qt - 1 - (int)blockIdx.x;  // heaviest query tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
+  // grid = (head, batch, tile): CTAs are dispatched x-fastest, so every (head, batch) pair's heaviest causal tile is
+  // handed out before any lighter one (longest-processing-time order: ~95 % slot efficiency instead of ~74 % when the
+  // tile index varies fastest)
+  const int qt = n_qt - 1 - (int)blockIdx.z;  // heaviest query tiles first
+  const int h = blockIdx.x, b = blockIdx.y;
   const int g = h / (H / KVH);
   const int q0 = qt * AT_BR;
   const int row_base = b * T;                 // row of this sequence in the [B*T, ld] activation
@@ -282,7 +285,7 @@ int sk_attn_tc_fwd_launch(const bf16* qkv, bf16* o, float* lse, int B, int T, in
     SK_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     init = true;
   }
-  dim3 grid((T + AT_BR - 1) / AT_BR, H, B);
+  dim3 grid(H, B, (T + AT_BR - 1) / AT_BR);   // tile index slowest: see the kernel's note on dispatch order
   sk_prof_begin(1, s);
   if (causal) attn_tc_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, s>>>(tm, o, lse, T, ldo, H, KVH, scale);
   else attn_tc_fwd_kernel<false><<<grid, AT_THREADS, AT_SMEM, s>>>(tm, o, lse, T, ldo, H, KVH, scale);
@@ -582,8 +585,8 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = (T + AT_BR - 1) / AT_BR;
-  const int qt = n_qt - 1 - (int)blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int qt = n_qt - 1 - (int)blockIdx.z;   // heaviest query tiles first, tile index slowest (see the forward)
+  const int h = blockIdx.x, b = blockIdx.y;
   const int g = h / (H / KVH);
   const int q0 = qt * AT_BR;
   const int row_base = b * T;
@@ -685,8 +688,11 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     const float sl2 = scale * 1.4426950408889634f;
     const bool row_ok = qrow < T;
     const size_t soff = ((size_t)b * H + h) * T + (row_ok ? qrow : 0);
-    const float lse2 = row_ok ? lse[soff] * 1.4426950408889634f : 0.f;
-    const float del = row_ok ? delta[soff] : 0.f;
+    // packed-pair math (two keys per instruction): p = 2^(s*sl2 - lse2), dS' = p * (dP - delta); the 1/sqrt(d) factor of
+    // dS is applied once to dQ in the epilogue instead of to every score
+    const f32x2 nlse2 = dup2(row_ok ? -lse[soff] * 1.4426950408889634f : 0.f);
+    const f32x2 del2 = dup2(row_ok ? delta[soff] : 0.f);
+    const f32x2 sl22 = dup2(sl2);
     for (int j = 0; j < n_kv; ++j) {
       const int k0 = j * BQ_BC;
       mbar_wait(sdp_full, j & 1);
@@ -699,21 +705,22 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
       const bool need_mask = (CAUSAL && k0 + BQ_BC - 1 > q0) || (k0 + BQ_BC > T) || (q0 + AT_BR > T);
-      mbar_wait(ds_empty, (j & 1) ^ 1u);         // previous dQ MMA finished reading the dS buffer
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), sl2, -lse2));
-        float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -lse2));
+        float x0, x1;
+        upk2(fma2(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl22, nlse2), x0, x1);
+        float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
         if (need_mask) {
           const int key = k0 + half * 32 + 2 * i;
           if (!row_ok || key >= T || (CAUSAL && key > qrow)) p0 = 0.f;
           if (!row_ok || key + 1 >= T || (CAUSAL && key + 1 > qrow)) p1 = 0.f;
         }
-        const float d0 = p0 * (__uint_as_float(dv[2 * i]) - del) * scale;
-        const float d1 = p1 * (__uint_as_float(dv[2 * i + 1]) - del) * scale;
+        float d0, d1;
+        upk2(mul2(pk2(p0, p1), sub2(pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), del2)), d0, d1);
         pk[i] = pack_bf16(d0, d1);
       }
+      mbar_wait(ds_empty, (j & 1) ^ 1u);         // previous dQ MMA finished reading the dS buffer (the math above overlaps it)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int chunk = half * 4 + u;          // 8 chunks of 8 keys in the 64-key row
@@ -737,10 +744,10 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint4 w;
-          w.x = pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1]));
-          w.y = pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3]));
-          w.z = pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]));
-          w.w = pack_bf16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]));
+          w.x = pack_bf16(__uint_as_float(v[8 * u]) * scale, __uint_as_float(v[8 * u + 1]) * scale);
+          w.y = pack_bf16(__uint_as_float(v[8 * u + 2]) * scale, __uint_as_float(v[8 * u + 3]) * scale);
+          w.z = pack_bf16(__uint_as_float(v[8 * u + 4]) * scale, __uint_as_float(v[8 * u + 5]) * scale);
+          w.w = pack_bf16(__uint_as_float(v[8 * u + 6]) * scale, __uint_as_float(v[8 * u + 7]) * scale);
           stg128(op + half * 32 + u * 8, w);
         }
       }
@@ -772,8 +779,8 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* stat_ptr = reinterpret_cast<float*>(smem_raw + (sStat - smem_u32(smem_raw)));   // [stage][lse|delta][64]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x;                   // key tile 0 has the most query tiles under the causal mask
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int kt = blockIdx.z;                   // key tile 0 has the most query tiles under the causal mask; tile index
+  const int h = blockIdx.x, b = blockIdx.y;    // slowest so the heavy tiles of every (head, batch) are dispatched first
   const int g = h / (H / KVH);
   const int k0 = kt * AT_BC;
   const int row_base = b * T;
@@ -869,19 +876,23 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     const int r = q * 32 + lane;                 // key row inside the tile == TMEM lane
     const int key = k0 + r;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const float sl2 = scale * 1.4426950408889634f;
+    const f32x2 sl22 = dup2(scale * 1.4426950408889634f);
     const int tid = threadIdx.x - 64;            // 0..255 among the element-wise warps
+    // the 64 lse / delta values of a query tile are per-COLUMN quantities here: staged in smem, [0,64): -lse * log2e,
+    // [64,128): delta.  Tile i+1's values are fetched into a register while tile i is processed, so the global-load
+    // latency is off the per-iteration critical path.
+    auto fetch_stat = [&](int it) -> float {
+      const int qq = (qt_begin + it) * BK_BR + (tid & 63);
+      const size_t off = ((size_t)b * H + h) * T + (qq < T ? qq : 0);
+      return qq < T ? ((tid < 64) ? -lse[off] * 1.4426950408889634f : delta[off]) : 0.f;
+    };
+    if (n_it > 0 && tid < 128) stat_ptr[tid] = fetch_stat(0);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int i = 0; i < n_it; ++i) {
       const int q0 = (qt_begin + i) * BK_BR;
-      // stage the 64 lse / delta values of this query tile (per-COLUMN quantities here) in smem
-      float* st_lse = stat_ptr + (i & 1) * 128;
-      if (tid < 128) {
-        const int qq = q0 + (tid & 63);
-        const size_t off = ((size_t)b * H + h) * T + (qq < T ? qq : 0);
-        const float val = qq < T ? ((tid < 64) ? lse[off] * 1.4426950408889634f : delta[off]) : 0.f;
-        st_lse[tid] = val;                       // [0,64): lse * log2e, [64,128): delta
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* st_lse = stat_ptr + (i & 1) * 128;
+      float stat_next = 0.f;
+      if (i + 1 < n_it && tid < 128) stat_next = fetch_stat(i + 1);
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
       uint32_t sv[32], dv[32];
@@ -892,24 +903,27 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
       const bool need_mask = (CAUSAL && q0 < k0 + AT_BC) || (q0 + BK_BR > T) || (k0 + AT_BC > T);
-      mbar_wait(pds_empty, (i & 1) ^ 1u);        // previous dV / dK MMAs finished reading P^T / dS^T
       uint32_t pp[16], pd[16];
+      // packed-pair math (two queries per instruction); dS'^T omits the 1/sqrt(d) factor, applied to dK in the epilogue
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int qi = half * 32 + 2 * e;
-        const float2 l2 = *reinterpret_cast<const float2*>(st_lse + qi);
-        const float2 dl = *reinterpret_cast<const float2*>(st_lse + 64 + qi);
-        float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), sl2, -l2.x));
-        float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), sl2, -l2.y));
+        const f32x2 nl2 = *reinterpret_cast<const f32x2*>(st_lse + qi);
+        const f32x2 dl = *reinterpret_cast<const f32x2*>(st_lse + 64 + qi);
+        float x0, x1;
+        upk2(fma2(pk2(__uint_as_float(sv[2 * e]), __uint_as_float(sv[2 * e + 1])), sl22, nl2), x0, x1);
+        float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
         if (need_mask) {
           const int qrow = q0 + qi;
           if (key >= T || qrow >= T || (CAUSAL && key > qrow)) p0 = 0.f;
           if (key >= T || qrow + 1 >= T || (CAUSAL && key > qrow + 1)) p1 = 0.f;
         }
         pp[e] = pack_bf16(p0, p1);
-        pd[e] = pack_bf16(p0 * (__uint_as_float(dv[2 * e]) - dl.x) * scale,
-                          p1 * (__uint_as_float(dv[2 * e + 1]) - dl.y) * scale);
+        float d0, d1;
+        upk2(mul2(pk2(p0, p1), sub2(pk2(__uint_as_float(dv[2 * e]), __uint_as_float(dv[2 * e + 1])), dl)), d0, d1);
+        pd[e] = pack_bf16(d0, d1);
       }
+      mbar_wait(pds_empty, (i & 1) ^ 1u);        // previous dV / dK MMAs finished reading P^T / dS^T (overlapped by the math)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int chunk = half * 4 + u;
@@ -922,6 +936,10 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      if (i + 1 < n_it) {
+        if (tid < 128) stat_ptr[((i + 1) & 1) * 128 + tid] = stat_next;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
     }
     // epilogue: fp32 partial dK | dV rows of this (batch, head, key)
     if (n_it > 0) {
@@ -940,10 +958,12 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
         for (int e = 0; e < 32; ++e) v[e] = 0u;
       }
       if (key < T) {
+        const float cs = c < 2 ? scale : 1.0f;     // dK columns carry the deferred 1/sqrt(d)
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          *reinterpret_cast<float4*>(pp + c * 32 + u * 4) = make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]),
-                                                                      __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+          *reinterpret_cast<float4*>(pp + c * 32 + u * 4) =
+              make_float4(__uint_as_float(v[4 * u]) * cs, __uint_as_float(v[4 * u + 1]) * cs,
+                          __uint_as_float(v[4 * u + 2]) * cs, __uint_as_float(v[4 * u + 3]) * cs);
       }
     }
   }
@@ -1004,7 +1024,7 @@ int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const
   }
   SK_TRY_RC(sk_attn_delta_launch(o, d_o, delta, B, T, H, ldo, s));
   sk_prof_begin(1, s);
-  dim3 g1((T + AT_BC - 1) / AT_BC, H, B), g2((T + AT_BR - 1) / AT_BR, H, B);
+  dim3 g1(H, B, (T + AT_BC - 1) / AT_BC), g2(H, B, (T + AT_BR - 1) / AT_BR);
   bf16* dq = dqkv;
   bf16* dk = dqkv + H * 64;
   bf16* dv = dqkv + (H + KVH) * 64;

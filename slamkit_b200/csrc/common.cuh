@@ -126,6 +126,39 @@ SK_DEVINL float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// ----------------------------------------------------------------------------------------------
+// Packed fp32 pairs (sm_100a FFMA2 / FMUL2 / FADD2): two fp32 lanes per instruction issue slot.  Same fp32 FLOP rate as
+// the scalar forms (profiles/r01_micro_ffma_vs_ffma2.txt); what they buy is issue bandwidth in element-wise code.
+// ----------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+SK_DEVINL f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+SK_DEVINL void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+SK_DEVINL f32x2 dup2(float c) { return pk2(c, c); }
+SK_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+SK_DEVINL f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+SK_DEVINL f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+SK_DEVINL f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 // Single-thread role waits (TMA producer / MMA issuer): back off with nanosleep so the spinning lane does not steal
 // issue slots from the compute warps sharing its scheduler.  Still bounded (trap after ~4 s).
 SK_DEVINL void mbar_wait_sleep(uint32_t bar, uint32_t parity) {

@@ -157,40 +157,10 @@ __global__ void conv0_affine_kernel(const double* __restrict__ stats, const floa
   affine[(size_t)b * C + c] = make_float2((float)sc, (float)((double)beta[c] - m * sc));
 }
 
-// Pass 2: out[b, t, c] = GELU(conv(x)[c,t] * scale + shift), channels-last, hi/lo bf16.  A thread owns CPT fixed
-// channels (their CPT x KW taps and affine pairs live in registers for the whole kernel) and walks over frames; a warp
-// covers 32*CPT consecutive channels of one frame (coalesced 8- or 16-byte stores per thread).  No shared memory.
-// CPT = 4 keeps the kernel under 85 registers -> 3 CTAs (24 warps) per SM, which is what hides the MUFU / FMA chains.
-// F2 = true pairs adjacent channels in packed fp32 registers so the 10 conv taps issue as 5 FFMA2 per channel pair
-// (same fp32 FMA chain per channel, half the issue slots; FFMA2 has no higher FLOP rate than FFMA on sm_100a --
-// profiles/r01_micro_ffma_vs_ffma2.txt -- the gain is issue bandwidth).
-typedef unsigned long long f32x2;
-SK_DEVINL f32x2 pk2(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-SK_DEVINL void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-SK_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
-SK_DEVINL f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-SK_DEVINL f32x2 sub2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-SK_DEVINL f32x2 dup2(float c) { return pk2(c, c); }
 // gelu_fast on NP packed pairs, written stage by stage so that the NP dependency chains (rcp -> 4 FMAs -> 2 muls ->
 // FMA, with a parallel mul -> mul -> ex2) interleave in the instruction stream: 10 packed FMA-pipe instructions, 4 MUFU,
-// 4 ALU per pair.  na = -|y| comes from OR-ing the sign bit, so t = 1 + p|y| = fma(-p, na, 1) and the tail is fma(na, q, relu(y)).
+// 4 ALU per pair.  na = -|y| comes from OR-ing the sign bit, so t = 1 + p|y| = fma(-p, na, 1) and the tail is
+// fma(na, q, relu(y)).
 template <int NP>
 SK_DEVINL void gelu_fast_pairs(f32x2 (&y)[NP]) {
   f32x2 na[NP], t[NP], e[NP], s[NP], r[NP];
@@ -237,6 +207,12 @@ SK_DEVINL void gelu_fast_pairs(f32x2 (&y)[NP]) {
   for (int i = 0; i < NP; ++i) y[i] = fma2(na[i], s[i], r[i]);
 }
 
+// Pass 2 (generic geometry): out[b, t, c] = GELU(conv(x)[c,t] * scale + shift), channels-last, hi/lo bf16.  A thread
+// owns CPT fixed channels (their CPT x KW taps, pre-multiplied by the GroupNorm scale, live in registers for the whole
+// kernel; the shift seeds the accumulator) and walks over frames; a warp covers 32*CPT consecutive channels of one
+// frame (coalesced 16-byte stores per thread).  No shared memory.  F2 = true pairs adjacent channels in packed fp32
+// registers so the 10 taps issue as 5 FFMA2 per channel pair (same fp32 FMA chain per channel, half the issue slots).
+// HuBERT's own front (kernel 10, stride 5) takes conv0_apply_k10s5_kernel below instead.
 template <int CPT, bool F2>
 __global__ void __launch_bounds__(256, 2)
 conv0_apply_kernel(const float* __restrict__ wav, const float* __restrict__ w, const float2* __restrict__ affine,
