@@ -33,7 +33,7 @@ struct GemmParams {
   int M, N, K;          // M = rows per batch item when batch > 1
   int batch;            // > 1: A is a 3-D tensor map (k, m, b) and C rows are b*M + m (conv layers, positional conv)
   int a_mode;           // 0: A tile at (kb*64, m0[, b]);  1: shifted window (n_blk*64, m0 + kb, b) (grouped pos-conv)
-  int passes;           // 1, or 3 = split-bf16 (A_hi*B_hi + A_hi*B_lo + A_lo*B_hi): fp32-grade products on bf16 pipes
+  int passes;           // 1, or 3 = split-bf16 (A_hi*B_hi + A_hi*B_lo + A_lo*B_hi per k-block): fp32-grade products on bf16 pipes
   void* C;
   void* C_lo;           // non-null: write (hi, lo) bf16 pair, lo = bf16(v - hi)
   int ldc;
@@ -315,7 +315,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer =====
+    // Split-bf16 mode (passes == 3) pairs two ring slots per k-block: [A_hi | B_hi] [A_lo | B_lo] are fetched once and
+    // feed all three products (hi*hi, hi*lo, lo*hi) -- 4 tile loads per k-block instead of the 6 that three separate
+    // passes over K would issue.
     if (lane == 0) {
+      const bool split = p.passes == 3;
+      const int n_stage = split ? Cfg::STAGES / 2 : Cfg::STAGES;
+      const uint32_t stage_bytes = split ? 2u * Cfg::STAGE_BYTES : (uint32_t)Cfg::STAGE_BYTES;
       int stage = 0;
       uint32_t phase = 0;
       WorkIter<SK> w(p, num_kb_total, kb_per_split, total_items);
@@ -325,15 +331,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m0 = (r / p.tiles_n) * BM;
         const int n_blk = r % p.tiles_n;
         const int n0 = n_blk * BN;
-        for (int pass = 0; pass < p.passes; ++pass) {
-          const CUtensorMap* mapA = (pass == 2) ? &tmA_lo : &tmA;
-          const CUtensorMap* mapB = (pass == 1) ? &tmB_lo : &tmB;
-          for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+        for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t fb = full_bar(stage);
+          mbar_arrive_expect_tx(fb, split ? 2u * STAGE_TX : STAGE_TX);
+          for (int part = 0; part < (split ? 2 : 1); ++part) {
+            const CUtensorMap* mapA = part ? &tmA_lo : &tmA;
+            const CUtensorMap* mapB = part ? &tmB_lo : &tmB;
+            const uint32_t sA = smem_base + stage * stage_bytes + part * Cfg::STAGE_BYTES;
             const uint32_t sB = sA + Cfg::A_BYTES;
-            const uint32_t fb = full_bar(stage);
-            mbar_arrive_expect_tx(fb, STAGE_TX);
             if (!A_MN) {
               if (p.a_mode & 2) {
                 if (p.a_mode & 1) tma_load_3d(sA, mapA, fb, n_blk * 64, m0 + kb, bidx);
@@ -351,8 +357,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int j = 0; j < Cfg::B_ATOMS; ++j) tma_load_2d(sB + j * (BK * 128), mapB, fb, n0 + 64 * j, kb * BK);
             }
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
           }
+          if (++stage == n_stage) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -360,6 +366,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(1u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, BM, BN);
+      const bool split = p.passes == 3;
+      const int n_stage = split ? Cfg::STAGES / 2 : Cfg::STAGES;
+      const uint32_t stage_bytes = split ? 2u * Cfg::STAGE_BYTES : (uint32_t)Cfg::STAGE_BYTES;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -369,22 +378,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
-        const int k_iters = max(0, w.kb_end - w.kb_begin) * p.passes;
+        const int k_iters = max(0, w.kb_end - w.kb_begin);
         for (int kb = 0; kb < k_iters; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + Cfg::A_BYTES;
+          const uint32_t s_hi = smem_base + stage * stage_bytes;
+          // products per k-block: hi*hi, then (split mode) hi*lo and lo*hi
+          for (int g = 0; g < (split ? 3 : 1); ++g) {
+            const uint32_t sA = s_hi + (g == 2 ? Cfg::STAGE_BYTES : 0);
+            const uint32_t sB = s_hi + Cfg::A_BYTES + (g == 1 ? Cfg::STAGE_BYTES : 0);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = A_MN ? umma_desc_sw128(sA + k * (UMMA_K * 128), BK * 128, 1024)
-                                        : umma_desc_sw128(sA + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_desc_sw128(sB + k * (UMMA_K * 128), BK * 128, 1024)
-                                        : umma_desc_sw128(sB + k * (UMMA_K * 2), 16, 1024);
-            tc_mma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = A_MN ? umma_desc_sw128(sA + k * (UMMA_K * 128), BK * 128, 1024)
+                                          : umma_desc_sw128(sA + k * (UMMA_K * 2), 16, 1024);
+              const uint64_t bdesc = B_MN ? umma_desc_sw128(sB + k * (UMMA_K * 128), BK * 128, 1024)
+                                          : umma_desc_sw128(sB + k * (UMMA_K * 2), 16, 1024);
+              tc_mma_f16(tmem_d, adesc, bdesc, idesc, (kb | g | k) != 0 ? 1u : 0u);
+            }
           }
           tc_commit(empty_bar(stage));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stage) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(as));
         as ^= 1;
