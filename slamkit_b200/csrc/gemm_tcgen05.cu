@@ -73,7 +73,21 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 };
 
-SK_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(erf) for the fused epilogue (HuBERT conv layers and FFN): branch-free Abramowitz-Stegun 7.1.26 erf, folded as
+//   gelu(y) = relu(y) - |y| * (P(t)/2) * exp(-y^2/2),  t = 1/(1 + p|y|/sqrt2)
+// |error| <= 1.5e-7 * |y|/2 absolute -- below the 2^-17 relative grid of the hi/lo bf16 outputs it feeds -- at a third of
+// the instructions of libdevice's two-branch erff (same form as hubert_kernels.cu's conv0 front).
+SK_DEVINL float gelu_erf(float y) {
+  const float a = fabsf(y);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, a, 1.0f)));
+  float s = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  s = fmaf(s, t, 0.5f * 1.421413741f);
+  s = fmaf(s, t, 0.5f * -0.284496736f);
+  s = fmaf(s, t, 0.5f * 0.254829592f);
+  const float e = ex2_approx((y * y) * -0.72134752044448170368f);
+  return fmaf(-a, (s * t) * e, fmaxf(y, 0.0f));
+}
 
 // Work scheduler shared by the three warp roles.
 //

@@ -121,9 +121,12 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16*
   }
 }
 
-// backward: g = dy*w ; xhat = x*rstd ; dx = rstd*(g - xhat*mean(g*xhat)) (+ dres) ; dw partial = sum_rows dy*bf16(xhat)
+// backward: g = bf16(dy*w) ; xhat = x*rstd ; dx = rstd*g - rstd^2*mean(g*xhat)*x (+ dres) ; dw partial = sum_rows dy*bf16(xhat)
 // grid-stride over rows so every block owns a fixed slice; per-block partial dw rows are written to `dw_partial`
-// [gridDim.x, D] and reduced by rmsnorm_dw_reduce_kernel in a fixed order (deterministic).
+// [gridDim.x, D] and reduced by colsum_reduce_kernel in a fixed order (deterministic).
+// All three row operands (x, dy, dres) are requested before anything is consumed, g is formed by one packed bf16
+// multiply per pair (HMUL2.BF16: the exact product rounded once, the same value as rounding the fp32 product) and
+// kept packed for the second phase.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2)
 rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                    const float* __restrict__ rstd_in, const bf16* __restrict__ dres, bf16* __restrict__ dx,
@@ -140,62 +143,63 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
 #pragma unroll
   for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
     const int c = lane + 32 * j;
-    if (c < nvec) wv[j] = ldg128(w + c * 8);
+    wv[j] = c < nvec ? ldg128(w + c * 8) : make_uint4(0, 0, 0, 0);
   }
   for (int row = blockIdx.x * WARPS_PER_BLOCK + warp; row < M; row += gridDim.x * WARPS_PER_BLOCK) {
-    const float rstd = rstd_in[row];
-    uint4 xq[MAX_VEC_PER_LANE], dq[MAX_VEC_PER_LANE];   // packed bf16: kept raw to stay under 96 registers
-    float dot = 0.f;
+    uint4 xq[MAX_VEC_PER_LANE], gq[MAX_VEC_PER_LANE], rq[MAX_VEC_PER_LANE];   // packed bf16 (gq: dy, then g = dy*w)
 #pragma unroll
     for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
       const int c = lane + 32 * j;
       if (c < nvec) {
         xq[j] = ldg128_stream(x + (size_t)row * D + c * 8);
-        dq[j] = ldg128_stream(dy + (size_t)row * D + c * 8);
-        const uint32_t xu[4] = {xq[j].x, xq[j].y, xq[j].z, xq[j].w};
-        const uint32_t du[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
-        const uint32_t wu[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 xf = unpack_bf16(xu[k]);
-          const float2 df = unpack_bf16(du[k]);
-          const float2 wf = unpack_bf16(wu[k]);
-          const float xh0 = xf.x * rstd, xh1 = xf.y * rstd;
-          dot += bf16_round(df.x * wf.x) * xh0 + bf16_round(df.y * wf.y) * xh1;
-          dwacc[j][2 * k] += df.x * bf16_round(xh0);
-          dwacc[j][2 * k + 1] += df.y * bf16_round(xh1);
-        }
+        gq[j] = ldg128_stream(dy + (size_t)row * D + c * 8);
+        rq[j] = dres ? ldg128_stream(dres + (size_t)row * D + c * 8) : make_uint4(0, 0, 0, 0);
       }
     }
-    dot = warp_sum(dot) / (float)D;
+    const float rstd = rstd_in[row];
+    float dot = 0.f;
 #pragma unroll
     for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
       const int c = lane + 32 * j;
       if (c < nvec) {
         const uint32_t xu[4] = {xq[j].x, xq[j].y, xq[j].z, xq[j].w};
-        const uint32_t du[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
+        uint32_t du[4] = {gq[j].x, gq[j].y, gq[j].z, gq[j].w};
         const uint32_t wu[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
-        float o[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 xf = unpack_bf16(xu[k]);
           const float2 df = unpack_bf16(du[k]);
-          const float2 wf = unpack_bf16(wu[k]);
-          o[2 * k] = rstd * (bf16_round(df.x * wf.x) - xf.x * rstd * dot);
-          o[2 * k + 1] = rstd * (bf16_round(df.y * wf.y) - xf.y * rstd * dot);
+          const float xh0 = xf.x * rstd, xh1 = xf.y * rstd;
+          const float2 xb = unpack_bf16(pack_bf16(xh0, xh1));          // bf16(xhat): what the forward multiplied by w
+          dwacc[j][2 * k] = fmaf(df.x, xb.x, dwacc[j][2 * k]);
+          dwacc[j][2 * k + 1] = fmaf(df.y, xb.y, dwacc[j][2 * k + 1]);
+          bf162 gp = __hmul2(*reinterpret_cast<const bf162*>(&du[k]), *reinterpret_cast<const bf162*>(&wu[k]));
+          du[k] = *reinterpret_cast<uint32_t*>(&gp);
+          const float2 gf = unpack_bf16(du[k]);
+          dot = fmaf(gf.x, xh0, dot);
+          dot = fmaf(gf.y, xh1, dot);
         }
-        if (dres) {
-          const uint4 rv = ldg128_stream(dres + (size_t)row * D + c * 8);
-          const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+        gq[j] = make_uint4(du[0], du[1], du[2], du[3]);
+      }
+    }
+    dot = warp_sum(dot) / (float)D;
+    const float c2 = -(rstd * rstd) * dot;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 rf = unpack_bf16(ru[k]);
-            o[2 * k] += rf.x;
-            o[2 * k + 1] += rf.y;
-          }
+    for (int j = 0; j < MAX_VEC_PER_LANE; ++j) {
+      const int c = lane + 32 * j;
+      if (c < nvec) {
+        const uint32_t xu[4] = {xq[j].x, xq[j].y, xq[j].z, xq[j].w};
+        const uint32_t gu[4] = {gq[j].x, gq[j].y, gq[j].z, gq[j].w};
+        const uint32_t ru[4] = {rq[j].x, rq[j].y, rq[j].z, rq[j].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 xf = unpack_bf16(xu[k]);
+          const float2 gf = unpack_bf16(gu[k]);
+          const float2 rf = unpack_bf16(ru[k]);
+          o[k] = pack_bf16(fmaf(c2, xf.x, rstd * gf.x) + rf.x, fmaf(c2, xf.y, rstd * gf.y) + rf.y);
         }
-        stg128(dx + (size_t)row * D + c * 8,
-               make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7])));
+        stg128(dx + (size_t)row * D + c * 8, make_uint4(o[0], o[1], o[2], o[3]));
       }
     }
   }
@@ -306,24 +310,46 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos
 // ------------------------------------------------------------------------------------------------
 // SwiGLU: gu = [gate | up] (each F wide).  act = bf16(bf16(silu(g)) * u)
 // ------------------------------------------------------------------------------------------------
-SK_DEVINL float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// sigmoid via ex2.approx + rcp.approx (relative error ~2e-7, far inside the bf16 rounding every use here ends in)
+SK_DEVINL float sigmoid_f(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(x * -1.4426950408889634f)));
+  return r;
+}
+SK_DEVINL float silu_f(float x) { return x * sigmoid_f(x); }
 
-__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int M, int F) {
+// two independent 16-byte vectors per thread and iteration (more loads in flight per thread)
+__global__ void __launch_bounds__(256)
+swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int M, int F) {
   const int vec_per_row = F / 8;
   const long total = (long)M * vec_per_row;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int m = (int)(i / vec_per_row);
-    const int c = (int)(i % vec_per_row);
-    const uint4 gv = ldg128_stream(gu + (size_t)m * 2 * F + c * 8);
-    const uint4 uv = ldg128_stream(gu + (size_t)m * 2 * F + F + c * 8);
-    const uint32_t g[4] = {gv.x, gv.y, gv.z, gv.w}, u[4] = {uv.x, uv.y, uv.z, uv.w};
-    uint32_t o[4];
+  const long half = (total + 1) / 2;
+  for (long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x; i0 < half; i0 += (long)gridDim.x * blockDim.x) {
+    uint4 gv[2], uv[2];
+    long idx[2] = {i0, i0 + half};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 gf = unpack_bf16(g[k]), uf = unpack_bf16(u[k]);
-      o[k] = pack_bf16(bf16_round(silu_f(gf.x)) * uf.x, bf16_round(silu_f(gf.y)) * uf.y);
+    for (int v = 0; v < 2; ++v) {
+      if (idx[v] < total) {
+        const int m = (int)(idx[v] / vec_per_row), c = (int)(idx[v] % vec_per_row);
+        gv[v] = ldg128_stream(gu + (size_t)m * 2 * F + c * 8);
+        uv[v] = ldg128_stream(gu + (size_t)m * 2 * F + F + c * 8);
+      }
     }
-    stg128(act + (size_t)m * F + c * 8, make_uint4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      if (idx[v] < total) {
+        const int m = (int)(idx[v] / vec_per_row), c = (int)(idx[v] % vec_per_row);
+        const uint32_t g[4] = {gv[v].x, gv[v].y, gv[v].z, gv[v].w}, u[4] = {uv[v].x, uv[v].y, uv[v].z, uv[v].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 gf = unpack_bf16(g[k]), uf = unpack_bf16(u[k]);
+          const float2 sb = unpack_bf16(pack_bf16(silu_f(gf.x), silu_f(gf.y)));   // bf16(silu(g))
+          o[k] = pack_bf16(sb.x * uf.x, sb.y * uf.y);
+        }
+        stg128(act + (size_t)m * F + c * 8, make_uint4(o[0], o[1], o[2], o[3]));
+      }
+    }
   }
 }
 
@@ -343,7 +369,7 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __res
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 gf = unpack_bf16(g[k]), uf = unpack_bf16(u[k]), df = unpack_bf16(d[k]);
-      const float s0 = 1.0f / (1.0f + __expf(-gf.x)), s1 = 1.0f / (1.0f + __expf(-gf.y));
+      const float s0 = sigmoid_f(gf.x), s1 = sigmoid_f(gf.y);
       const float sil0 = bf16_round(gf.x * s0), sil1 = bf16_round(gf.y * s1);
       const float ds0 = s0 * (1.0f + gf.x * (1.0f - s0)), ds1 = s1 * (1.0f + gf.y * (1.0f - s1));
       // d(silu)*u rounded like the bf16 autograd chain: d_silu = bf16(dact*u); dg = bf16(d_silu * silu'(g))
@@ -677,7 +703,7 @@ int sk_rope_launch(bf16* qkv, const bf16* cos_t, const bf16* sin_t, const int* p
 }
 int sk_swiglu_fwd_launch(const bf16* gu, bf16* act, int M, int F, cudaStream_t s) {
   SK_REQUIRE(F % 8 == 0, "swiglu: F must be a multiple of 8");
-  swiglu_fwd_kernel<<<grid_for((long)M * F / 8, 256), 256, 0, s>>>(gu, act, M, F);
+  swiglu_fwd_kernel<<<grid_for(((long)M * F / 8 + 1) / 2, 256), 256, 0, s>>>(gu, act, M, F);
   SK_LAUNCH_CHECK();
   return 0;
 }
