@@ -210,7 +210,10 @@ def run_hubert_gpu(args, rank, local_rank, world, lib, dist):
         gbs = conv0_bytes / (ms[3] / 1e3) / 1e9 if ms[3] > 0 else None
         out["roofline"] = {"bound": "hbm", "kernel": "conv0_apply_kernel (conv0 + GroupNorm + GELU, hi/lo channels-last)",
                            "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                           "frac": (gbs / pk["hbm_gbs"]) if gbs else None, "traffic": None,
+                           "frac": (gbs / pk["hbm_gbs"]) if gbs else None,
+                           # ncu --set full at batch 16: 3.086 GB written + 0.031 GB read per launch -> x4 at batch 64
+                           "traffic": 4 * (3.0860e9 + 0.0315e9), "traffic_unit": "bytes/launch",
+                           "traffic_source": "profiles/r01_ncu_conv0_apply_v4.txt (batch 16, scaled x4)",
                            "algorithmic_bytes_per_launch": conv0_bytes, "peak_source": pk["source"],
                            "breakdown_ms": {"gemm": ms[0], "attention": ms[1], "conv0_apply": ms[3],
                                             "batch": dev_ms / n},
@@ -365,7 +368,11 @@ def main():
         gemm_tf = GEMM_FLOP_PER_TOKEN * PER_GPU_BATCH * SEQ / (gemm_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel ({cnt[0] // reps} launches/step)",
                 "achieved": gemm_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": gemm_tf / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained",
+                "frac": gemm_tf / pk["bf16_sustained"],
+                # DRAM bytes per GEMM launch (read + write), mean over the step's GEMM launches, from the committed
+                # ncu capture profiles/r01_lm_step_launches_v3.txt (bench.py cannot run under ncu itself)
+                "traffic": 75.78e6, "traffic_unit": "bytes/launch", "traffic_source": "profiles/r01_lm_step_launches_v3.txt",
+                "peak_source": pk["source"] + ", sustained",
                 "algorithmic_flops_per_step": GEMM_FLOP_PER_TOKEN * PER_GPU_BATCH * SEQ,
                 "share_of_step": gemm_ms / step_ms,
                 "breakdown_ms": {"gemm": gemm_ms, "attention": attn_ms, "optimizer": opt_ms,

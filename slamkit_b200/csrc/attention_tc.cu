@@ -1035,6 +1035,8 @@ int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const
     attn_tc_bwd_dkdv_kernel<false><<<g1, BWD_THREADS, DKDV_SMEM, s>>>(tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale);
     attn_tc_bwd_dq_kernel<false><<<g2, BWD_THREADS, DQ_SMEM, s>>>(tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale);
   }
+  sk_count_launch();
+  sk_count_launch();                               // two kernels above; the reduce below is counted by SK_LAUNCH_CHECK
   const long total = (long)B * KVH * T * 16;
   int blocks = (int)((total + 255) / 256);
   if (blocks > sk_num_sms() * 8) blocks = sk_num_sms() * 8;

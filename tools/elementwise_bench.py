@@ -32,6 +32,9 @@ def report(name, us, nbytes):
     print(f"{name:16s} {us:7.1f} us   {nbytes / us / 1e3:7.0f} GB/s   {nbytes / us / 1e3 / PEAK:5.2f} of HBM peak", flush=True)
 
 
+# fixed cost of one launch + event pair in this harness (same kernel on 8 rows)
+_x = torch.randn(8, 896, device=dev).to(torch.bfloat16); _w = torch.ones(896, device=dev).to(torch.bfloat16)
+print(f"(harness floor: {timeit(lambda: ops.rmsnorm_fwd(_x, _w, 1e-6)):.1f} us per single-launch op)")
 M, D, F, QKV = 8192, 896, 4864, 1152
 bf = torch.bfloat16
 x = torch.randn(M, D, device=dev).to(bf); dy = torch.randn(M, D, device=dev).to(bf); dres = torch.randn(M, D, device=dev).to(bf)
