@@ -1,5 +1,6 @@
 // extern "C" surface of libslamkit_b200.so for the op-level entry points (see include/slamkit_b200.h), plus the
 // error / device-info plumbing.  The handle-level entry points live in lm_step.cu and hubert_step.cu.
+#include <stdlib.h>
 #include "kernels.h"
 #include "../../include/slamkit_b200.h"
 #include <atomic>
@@ -17,6 +18,10 @@ void sk_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool sk_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SK_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
 }
 void sk_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

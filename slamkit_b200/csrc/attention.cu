@@ -396,6 +396,8 @@ attn_fwd_split_kernel(const bf16* __restrict__ q_hi, const bf16* __restrict__ q_
 // ------------------------------------------------------------------------------------------------
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta,
                                   int B, int T, int H, int ldo) {
+  griddep_launch();
+  griddep_wait();
   const long total = (long)B * T * H * 8;  // 8 threads per (row, head)
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const bool ok = i < total;
@@ -699,7 +701,7 @@ int sk_attn_bwd_launch(const bf16* q, const bf16* k, const bf16* v, const bf16* 
   }
   const long total = (long)B * T * H * 8;
   sk_prof_begin(1, s);
-  attn_delta_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(o, d_o, delta, B, T, H, ldo);
+  SK_CUDA_CHECK(sk_launch_pdl(attn_delta_kernel, dim3((int)((total + 255) / 256)), dim3(256), (size_t)(0), s, o, d_o, delta, B, T, H, ldo));
   SK_LAUNCH_CHECK();
   const int group = H / KVH;
   dim3 g1((T + 63) / 64, KVH, B), g2((T + 63) / 64, H, B);
@@ -738,7 +740,7 @@ int sk_attn_fwd_split_launch(const bf16* q_hi, const bf16* q_lo, const bf16* k_h
 int sk_attn_delta_launch(const bf16* o, const bf16* d_o, float* delta, int B, int T, int H, int ldo, cudaStream_t s) {
   const long total = (long)B * T * H * 8;
   sk_prof_begin(1, s);
-  attn_delta_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(o, d_o, delta, B, T, H, ldo);
+  SK_CUDA_CHECK(sk_launch_pdl(attn_delta_kernel, dim3((int)((total + 255) / 256)), dim3(256), (size_t)(0), s, o, d_o, delta, B, T, H, ldo));
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;

@@ -43,6 +43,7 @@ template <bool CAUSAL>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ o, float* __restrict__ lse, int T, int ldo,
                    int H, int KVH, float scale) {
+  griddep_launch();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
@@ -89,6 +90,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_wait();   // prologue (barriers, TMEM) may overlap the previous kernel's tail; its outputs are visible from here
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
   if (warp == 0) {
@@ -287,8 +289,8 @@ int sk_attn_tc_fwd_launch(const bf16* qkv, bf16* o, float* lse, int B, int T, in
   }
   dim3 grid(H, B, (T + AT_BR - 1) / AT_BR);   // tile index slowest: see the kernel's note on dispatch order
   sk_prof_begin(1, s);
-  if (causal) attn_tc_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, s>>>(tm, o, lse, T, ldo, H, KVH, scale);
-  else attn_tc_fwd_kernel<false><<<grid, AT_THREADS, AT_SMEM, s>>>(tm, o, lse, T, ldo, H, KVH, scale);
+  if (causal) SK_CUDA_CHECK(sk_launch_pdl(attn_tc_fwd_kernel<true>, dim3(grid), dim3(AT_THREADS), (size_t)(AT_SMEM), s, tm, o, lse, T, ldo, H, KVH, scale));
+  else SK_CUDA_CHECK(sk_launch_pdl(attn_tc_fwd_kernel<false>, dim3(grid), dim3(AT_THREADS), (size_t)(AT_SMEM), s, tm, o, lse, T, ldo, H, KVH, scale));
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;
@@ -307,6 +309,7 @@ constexpr uint32_t ATS_SMEM = 2 * SQ_BYTES + 4 * SKV_BYTES + 2 * SKV_BYTES + 2 *
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_fwd_split_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL,
                          bf16* __restrict__ o_hi, bf16* __restrict__ o_lo, int T, int ldo, int H, float scale) {
+  griddep_launch();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQh = smem_base, sQl = sQh + SQ_BYTES;
@@ -347,6 +350,7 @@ attn_tc_fwd_split_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_wait();   // prologue (barriers, TMEM) may overlap the previous kernel's tail; its outputs are visible from here
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
   if (warp == 0) {
@@ -575,6 +579,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                       const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
                       const float* __restrict__ delta, bf16* __restrict__ dq, int T, int ldg, int H, int KVH, float scale) {
+  griddep_launch();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base, sdO = sQ + SQ_BYTES, sK = sdO + SQ_BYTES, sV = sK + 2 * T64_BYTES,
@@ -618,6 +623,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_wait();   // prologue (barriers, TMEM) may overlap the previous kernel's tail; its outputs are visible from here
   const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdQ = tmem_base + 128;
 
   if (warp == 0) {
@@ -770,6 +776,7 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
                         const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
                         const float* __restrict__ delta, float* __restrict__ partial /*[B][H][T][128]*/, int T, int H,
                         int KVH, float scale) {
+  griddep_launch();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = smem_base, sV = sK + SKV_BYTES, sQ = sV + SKV_BYTES /*[2]*/, sdO = sQ + 2 * T64_BYTES /*[2]*/,
@@ -812,6 +819,7 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_wait();   // prologue (barriers, TMEM) may overlap the previous kernel's tail; its outputs are visible from here
   const uint32_t tST = tmem_base, tdPT = tmem_base + 64, tdK = tmem_base + 128, tdV = tmem_base + 192;
 
   if (warp == 0) {
@@ -978,6 +986,8 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 // dk / dv (bf16, column slices of the fused gradient buffer) = sum over the GQA group's query heads, fixed order
 __global__ void attn_tc_group_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ dk, bf16* __restrict__ dv,
                                             int B, int T, int H, int KVH, int ldg) {
+  griddep_launch();
+  griddep_wait();
   const int group = H / KVH;
   const long total = (long)B * KVH * T * 16;      // 16 threads per (b, g, t): 8 columns each of the 128 (dK | dV)
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -1029,18 +1039,18 @@ int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const
   bf16* dk = dqkv + H * 64;
   bf16* dv = dqkv + (H + KVH) * 64;
   if (causal) {
-    attn_tc_bwd_dkdv_kernel<true><<<g1, BWD_THREADS, DKDV_SMEM, s>>>(tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale);
-    attn_tc_bwd_dq_kernel<true><<<g2, BWD_THREADS, DQ_SMEM, s>>>(tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale);
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dkdv_kernel<true>, dim3(g1), dim3(BWD_THREADS), (size_t)(DKDV_SMEM), s, tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale));
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dq_kernel<true>, dim3(g2), dim3(BWD_THREADS), (size_t)(DQ_SMEM), s, tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale));
   } else {
-    attn_tc_bwd_dkdv_kernel<false><<<g1, BWD_THREADS, DKDV_SMEM, s>>>(tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale);
-    attn_tc_bwd_dq_kernel<false><<<g2, BWD_THREADS, DQ_SMEM, s>>>(tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale);
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dkdv_kernel<false>, dim3(g1), dim3(BWD_THREADS), (size_t)(DKDV_SMEM), s, tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale));
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dq_kernel<false>, dim3(g2), dim3(BWD_THREADS), (size_t)(DQ_SMEM), s, tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale));
   }
   sk_count_launch();
   sk_count_launch();                               // two kernels above; the reduce below is counted by SK_LAUNCH_CHECK
   const long total = (long)B * KVH * T * 16;
   int blocks = (int)((total + 255) / 256);
   if (blocks > sk_num_sms() * 8) blocks = sk_num_sms() * 8;
-  attn_tc_group_reduce_kernel<<<blocks, 256, 0, s>>>(partial, dk, dv, B, T, H, KVH, ldg);
+  SK_CUDA_CHECK(sk_launch_pdl(attn_tc_group_reduce_kernel, dim3(blocks), dim3(256), (size_t)(0), s, partial, dk, dv, B, T, H, KVH, ldg));
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;

@@ -40,6 +40,39 @@ void sk_count_launch();
   } while (0)
 
 int sk_num_sms();
+
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The LM step is ~760 back-to-back launches on one stream; with the
+// programmatic-stream-serialization attribute a kernel's CTAs may become resident -- and run their prologue (barrier
+// init, TMEM allocation, tensor-map prefetch, index math) -- while the previous kernel's last wave drains.  Every
+// kernel launched this way calls griddep_wait() before its first global-memory access (the wait returns once the
+// previous grid has completed and its writes are visible), so data hazards are exactly those of plain stream order.
+// SK_PDL=0 in the environment turns the attribute off.
+// ----------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool sk_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t sk_launch_pdl_if(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && sk_pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t sk_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  return sk_launch_pdl_if(true, kernel, grid, block, smem, s, args...);
+}
 // bench-only device timing hooks (api.cu): category 0 = tcgen05 GEMM, 1 = attention, 2 = optimiser, 3 = other
 void sk_prof_begin(int cat, cudaStream_t s);
 void sk_prof_end(cudaStream_t s);

@@ -50,6 +50,7 @@ struct GemmParams {
   int splits;           // > 1: split-K; work item = (tile, split), fp32 partial tiles go to splitk_ws[split][M][N]
   float* splitk_ws;
   int tma_store;        // 1: bf16 output leaves through swizzled smem staging + cp.async.bulk.tensor stores (tmC)
+  int pdl;              // host-only: launch attribute
   int sk_units;         // > 0: stream-K over the first sk_units tile groups ("units", see WorkIter)
   int sk_groups;        // CTA groups that share the stream-K iteration space (each unit is cut into <= ~4 ranges)
   int sk_G;             // tiles per unit = CTAs per group (they run the same k-blocks in lockstep)
@@ -285,6 +286,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo,
                     const __grid_constant__ CUtensorMap tmC, GemmParams p) {
   using Cfg = GemmCfg<BN>;
+  griddep_launch();                 // the next kernel on the stream may start its own prologue now
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;   // 1024-byte aligned
@@ -326,6 +328,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_wait();                   // prologue done; inputs of this GEMM are complete and visible from here on
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -597,6 +600,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // C[m,n] = bf16( sum_s ws[s][m][n] ) (+ C when accumulate), fixed summation order -> deterministic split-K
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, bf16* __restrict__ C, int M, int N, int ldc, int splits,
                                      int accumulate) {
+  griddep_launch();
+  griddep_wait();
   const long total = (long)M * N / 8;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long e = i * 8;
@@ -692,8 +697,10 @@ int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream
     attr_set = true;
   }
   sk_prof_begin(0, stream);
-  gemm_tcgen05_kernel<BN, A_MN, B_MN, SK><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  cudaError_t lerr = sk_launch_pdl_if(p.pdl != 0, gemm_tcgen05_kernel<BN, A_MN, B_MN, SK>, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, stream,
+                                   tm[0], tm[1], tm[2], tm[3], tm[4], p);
   sk_prof_end(stream);
+  SK_CUDA_CHECK(lerr);
   SK_LAUNCH_CHECK();
   return 0;
 }
@@ -797,6 +804,7 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
   p.round_before_res = g.round_before_res;
   p.act = g.act;
   p.col_gin = g.col_gin; p.col_gout = g.col_gout;
+  p.pdl = g.pdl;
   const long tiles = (long)p.tiles_m * p.tiles_n * g.batch;
   // split-K: only for plain bf16-output GEMMs that leave most SMs idle and have a long K loop (the small wgrads)
   p.splits = 1;
@@ -872,8 +880,8 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
     int blocks = (int)((n8 + 255) / 256);
     if (blocks > nsm * 8) blocks = nsm * 8;
     sk_prof_begin(0, stream);
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.splitk_ws, reinterpret_cast<bf16*>(g.C), g.M, g.N, g.ldc, p.splits,
-                                                     g.residual != nullptr);
+    SK_CUDA_CHECK(sk_launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), (size_t)(0), stream, p.splitk_ws, reinterpret_cast<bf16*>(g.C), g.M, g.N, g.ldc, p.splits,
+                                                     g.residual != nullptr));
     sk_prof_end(stream);
     SK_LAUNCH_CHECK();
   }
@@ -893,6 +901,7 @@ int sk_gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const 
   g.C = C; g.ldc = ldc; g.out_f32 = out_f32;
   g.bias = bias; g.residual = residual; g.ldr = ldr; g.round_before_res = round_before_res; g.act = act;
   g.force_bn = force_bn;
+  g.pdl = 1;
   g.splitk_ws = splitk_ws;
   g.splitk_ws_bytes = splitk_ws_bytes;
   return sk_gemm_ex_launch(g, stream);

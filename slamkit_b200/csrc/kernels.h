@@ -32,6 +32,7 @@ struct SkGemmEx {
   int force_bn;
   void* splitk_ws;          // optional scratch: deterministic split-K (few tiles, long K) and stream-K load balancing
   size_t splitk_ws_bytes;
+  int pdl;                  // 1: launch with programmatic stream serialization (the LM step's short back-to-back GEMMs)
 };
 int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream);
 int sk_gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,

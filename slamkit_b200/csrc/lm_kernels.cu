@@ -80,6 +80,8 @@ __global__ void add_f32_into_bf16_kernel(bf16* __restrict__ grad, const float* _
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                    float* __restrict__ rstd_out, int M, int D, float eps) {
+  griddep_launch();
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS_PER_BLOCK + warp;
   if (row >= M) return;
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2)
 rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                    const float* __restrict__ rstd_in, const bf16* __restrict__ dres, bf16* __restrict__ dx,
                    float* __restrict__ dw_partial, int M, int D) {
+  griddep_launch();
+  griddep_wait();
   extern __shared__ float sdw[];  // [WARPS_PER_BLOCK][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D / 8;
@@ -225,6 +229,8 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
 // every thread sums a fixed strided subset of rows, then a fixed-order tree over the 32 groups (deterministic).
 __global__ void __launch_bounds__(1024)
 colsum_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int nblocks, int D, int accumulate) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float sred[32][33];
   const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + c;
@@ -247,6 +253,8 @@ colsum_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ out, 
 
 // column sums of a bf16 [M, N] matrix (leading dim ld) -> partial[gridDim.y][N]; used for the q/k/v bias gradient
 __global__ void colsum_partial_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int M, int N, int ld) {
+  griddep_launch();
+  griddep_wait();
   const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (col >= N) return;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -276,6 +284,8 @@ __global__ void colsum_partial_kernel(const bf16* __restrict__ x, float* __restr
 __global__ void rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
                             const int* __restrict__ pos_ids, int M, int T, int ld, int n_rot_heads, int head_dim,
                             int inverse) {
+  griddep_launch();
+  griddep_wait();
   const int half = head_dim / 2;          // 32
   const int vec_per_head = half / 8;      // 4 threads per (token, head)
   const long total = (long)M * n_rot_heads * vec_per_head;
@@ -321,6 +331,8 @@ SK_DEVINL float silu_f(float x) { return x * sigmoid_f(x); }
 // two independent 16-byte vectors per thread and iteration (more loads in flight per thread)
 __global__ void __launch_bounds__(256)
 swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int M, int F) {
+  griddep_launch();
+  griddep_wait();
   const int vec_per_row = F / 8;
   const long total = (long)M * vec_per_row;
   const long half = (total + 1) / 2;
@@ -356,6 +368,8 @@ swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int M, in
 // d_gu = [ d_act*u*silu'(g) | d_act*silu(g) ]
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dact, bf16* __restrict__ dgu,
                                   int M, int F) {
+  griddep_launch();
+  griddep_wait();
   const int vec_per_row = F / 8;
   const long total = (long)M * vec_per_row;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -663,7 +677,7 @@ int sk_embed_bwd_launch(const int64_t* ids, const bf16* dx, float* scratch, bf16
 }
 int sk_rmsnorm_fwd_launch(const bf16* x, const bf16* w, bf16* y, float* rstd, int M, int D, float eps, cudaStream_t s) {
   SK_REQUIRE(D % 8 == 0 && D <= 1024, "rmsnorm: D must be a multiple of 8 and <= 1024 (D=%d)", D);
-  rmsnorm_fwd_kernel<<<(M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, y, rstd, M, D, eps);
+  SK_CUDA_CHECK(sk_launch_pdl(rmsnorm_fwd_kernel, dim3((M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), dim3(WARPS_PER_BLOCK * 32), (size_t)(0), s, x, w, y, rstd, M, D, eps));
   SK_LAUNCH_CHECK();
   return 0;
 }
@@ -676,9 +690,9 @@ int sk_rmsnorm_bwd_launch(const bf16* dy, const bf16* x, const bf16* w, const fl
   const int need = (M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   if (blocks > need) blocks = need;
   const size_t smem = (size_t)WARPS_PER_BLOCK * D * sizeof(float);
-  rmsnorm_bwd_kernel<<<blocks, WARPS_PER_BLOCK * 32, smem, s>>>(dy, x, w, rstd, dres, dx, dw_partial, M, D);
+  SK_CUDA_CHECK(sk_launch_pdl(rmsnorm_bwd_kernel, dim3(blocks), dim3(WARPS_PER_BLOCK * 32), (size_t)(smem), s, dy, x, w, rstd, dres, dx, dw_partial, M, D));
   SK_LAUNCH_CHECK();
-  colsum_reduce_kernel<<<(D + 31) / 32, 1024, 0, s>>>(dw_partial, dw, blocks, D, accumulate_dw);
+  SK_CUDA_CHECK(sk_launch_pdl(colsum_reduce_kernel, dim3((D + 31) / 32), dim3(1024), (size_t)(0), s, dw_partial, dw, blocks, D, accumulate_dw));
   SK_LAUNCH_CHECK();
   return 0;
 }
@@ -687,29 +701,29 @@ extern "C" int sk_colsum_splits(void) { return COLSUM_SPLITS; }
 int sk_colsum_launch(const bf16* x, bf16* out, float* partial, int M, int N, int ld, int accumulate, cudaStream_t s) {
   SK_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
   dim3 grid((N / 8 + 127) / 128, COLSUM_SPLITS);
-  colsum_partial_kernel<<<grid, 128, 0, s>>>(x, partial, M, N, ld);
+  SK_CUDA_CHECK(sk_launch_pdl(colsum_partial_kernel, dim3(grid), dim3(128), (size_t)(0), s, x, partial, M, N, ld));
   SK_LAUNCH_CHECK();
-  colsum_reduce_kernel<<<(N + 31) / 32, 1024, 0, s>>>(partial, out, COLSUM_SPLITS, N, accumulate);
+  SK_CUDA_CHECK(sk_launch_pdl(colsum_reduce_kernel, dim3((N + 31) / 32), dim3(1024), (size_t)(0), s, partial, out, COLSUM_SPLITS, N, accumulate));
   SK_LAUNCH_CHECK();
   return 0;
 }
 int sk_rope_launch(bf16* qkv, const bf16* cos_t, const bf16* sin_t, const int* pos_ids, int M, int T, int ld,
                    int n_rot_heads, int head_dim, int inverse, cudaStream_t s) {
   SK_REQUIRE(head_dim % 16 == 0 && ld % 8 == 0, "rope: head_dim must be a multiple of 16");
-  rope_kernel<<<grid_for((long)M * n_rot_heads * (head_dim / 16), 256), 256, 0, s>>>(qkv, cos_t, sin_t, pos_ids, M, T, ld,
-                                                                                   n_rot_heads, head_dim, inverse);
+  SK_CUDA_CHECK(sk_launch_pdl(rope_kernel, dim3(grid_for((long)M * n_rot_heads * (head_dim / 16), 256)), dim3(256), (size_t)(0), s, qkv, cos_t, sin_t, pos_ids, M, T, ld,
+                                                                                   n_rot_heads, head_dim, inverse));
   SK_LAUNCH_CHECK();
   return 0;
 }
 int sk_swiglu_fwd_launch(const bf16* gu, bf16* act, int M, int F, cudaStream_t s) {
   SK_REQUIRE(F % 8 == 0, "swiglu: F must be a multiple of 8");
-  swiglu_fwd_kernel<<<grid_for(((long)M * F / 8 + 1) / 2, 256), 256, 0, s>>>(gu, act, M, F);
+  SK_CUDA_CHECK(sk_launch_pdl(swiglu_fwd_kernel, dim3(grid_for(((long)M * F / 8 + 1) / 2, 256)), dim3(256), (size_t)(0), s, gu, act, M, F));
   SK_LAUNCH_CHECK();
   return 0;
 }
 int sk_swiglu_bwd_launch(const bf16* gu, const bf16* dact, bf16* dgu, int M, int F, cudaStream_t s) {
   SK_REQUIRE(F % 8 == 0, "swiglu: F must be a multiple of 8");
-  swiglu_bwd_kernel<<<grid_for((long)M * F / 8, 256), 256, 0, s>>>(gu, dact, dgu, M, F);
+  SK_CUDA_CHECK(sk_launch_pdl(swiglu_bwd_kernel, dim3(grid_for((long)M * F / 8, 256)), dim3(256), (size_t)(0), s, gu, dact, dgu, M, F));
   SK_LAUNCH_CHECK();
   return 0;
 }
