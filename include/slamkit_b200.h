@@ -96,12 +96,19 @@ int sk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
 /* tcgen05 / TMEM implementation of the same forward (S and O accumulate in tensor memory, operands staged by TMA).
  * qkv points at the fused [B*T, ld] projection: H q-heads, then KVH k-heads, then KVH v-heads, 64 columns each. */
 int sk_attn_tc_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int KVH, int ld, int ldo, int causal,
-                   float scale, void* stream);
+                   float scale, const int32_t* seg_start, void* stream);
+/* Document bounds of packed batches (DataCollatorWithFlattening, slamkit/data/hf_dataset.py:61-62): a document starts at
+ * column 0 and wherever position_ids == 0, exactly how HF derives cu_seqlens for its varlen flash-attention path
+ * (HF:modeling_flash_attention_utils.py prepare_fa_kwargs_from_position_ids).  seg_start[b*T+t] = in-row index of the
+ * first token of t's document, seg_end = one past its last.  Passing them (NULL = one document per row) to
+ * sk_attn_tc_fwd / sk_attn_tc_bwd makes attention block-diagonal causal; key tiles outside a tile's documents are
+ * skipped. */
+int sk_seg_bounds(const int32_t* pos_ids, int32_t* seg_start, int32_t* seg_end, int B, int T, void* stream);
 /* tcgen05 backward: dqkv (same fused layout as qkv, pitch ldg) from d_o; delta fp32 [B,H,T] and partial fp32
  * [B,H,T,128] are caller scratch.  Deterministic (per-head partials reduced over the GQA group in a fixed order). */
 int sk_attn_tc_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, float* partial,
                    void* dqkv, int B, int T, int H, int KVH, int ld, int ldo, int ldg, int causal, float scale,
-                   void* stream);
+                   const int32_t* seg_start, const int32_t* seg_end, void* stream);
 int sk_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                 float* delta, void* dq, void* dk, void* dv, int B, int T, int H, int KVH, int ld, int ldo, int ldg,
                 int causal, float scale, void* stream);

@@ -159,16 +159,19 @@ int sk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
   return sk_attn_fwd_launch(CBF(q), CBF(k), CBF(v), BF(o), lse, B, T, H, KVH, ld, ldo, causal, scale, S(stream));
 }
 int sk_attn_tc_fwd(const void* qkv, void* o, float* lse, int B, int T, int H, int KVH, int ld, int ldo, int causal,
-                   float scale, void* stream) {
+                   float scale, const int32_t* seg_start, void* stream) {
   SK_REQUIRE(qkv && o, "sk_attn_tc_fwd: null argument");
-  return sk_attn_tc_fwd_launch(CBF(qkv), BF(o), lse, B, T, H, KVH, ld, ldo, causal, scale, S(stream));
+  return sk_attn_tc_fwd_launch(CBF(qkv), BF(o), lse, B, T, H, KVH, ld, ldo, causal, scale, S(stream), seg_start);
+}
+int sk_seg_bounds(const int32_t* pos_ids, int32_t* seg_start, int32_t* seg_end, int B, int T, void* stream) {
+  return sk_seg_bounds_launch(pos_ids, seg_start, seg_end, B, T, S(stream));
 }
 int sk_attn_tc_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, float* partial,
                    void* dqkv, int B, int T, int H, int KVH, int ld, int ldo, int ldg, int causal, float scale,
-                   void* stream) {
+                   const int32_t* seg_start, const int32_t* seg_end, void* stream) {
   SK_REQUIRE(qkv && o && d_o && lse && delta && partial && dqkv, "sk_attn_tc_bwd: null argument");
   return sk_attn_tc_bwd_launch(CBF(qkv), CBF(o), CBF(d_o), lse, delta, partial, BF(dqkv), B, T, H, KVH, ld, ldo, ldg, causal,
-                               scale, S(stream));
+                               scale, S(stream), seg_start, seg_end);
 }
 int sk_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                 float* delta, void* dq, void* dk, void* dv, int B, int T, int H, int KVH, int ld, int ldo, int ldg,

@@ -42,7 +42,7 @@ SK_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::
 template <bool CAUSAL>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ o, float* __restrict__ lse, int T, int ldo,
-                   int H, int KVH, float scale) {
+                   int H, int KVH, float scale, const int* __restrict__ seg_start) {
   griddep_launch();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -92,25 +92,31 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   const uint32_t tmem_base = *tmem_slot_ptr;
   griddep_wait();   // prologue (barriers, TMEM) may overlap the previous kernel's tail; its outputs are visible from here
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  // Packed batches (several documents in one row, position_ids restarting at 0): seg_start[token] is the in-row index of
+  // the first token of its document.  Keys before it are masked (block-diagonal causal attention, what HF's varlen
+  // flash-attention path computes from the same position_ids) and whole key tiles before the tile's first document
+  // are skipped (seg_start is non-decreasing along a row, so the first query row has the smallest bound).
+  const int j_begin = seg_start ? seg_start[row_base + q0] / AT_BC : 0;
+  const int n_it = n_kv - j_begin;             // loop counters below start at 0 (barrier parities), tile index = j_begin + jj
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, SQ_BYTES);
       tma_load_2d(sQ, &tmQKV, q_full, h * 64, row_base + q0);
-      for (int j = 0; j < n_kv; ++j) {
+      for (int j = 0; j < n_it; ++j) {
         const int st = j & 1;
         mbar_wait_sleep(k_empty + 8 * st, ((j >> 1) & 1) ^ 1u);
         mbar_arrive_expect_tx(k_full + 8 * st, SKV_BYTES);
-        tma_load_2d(sK + st * SKV_BYTES, &tmQKV, k_full + 8 * st, (H + g) * 64, row_base + j * AT_BC);
+        tma_load_2d(sK + st * SKV_BYTES, &tmQKV, k_full + 8 * st, (H + g) * 64, row_base + (j_begin + j) * AT_BC);
         if (j >= 1) {   // V_{j-1} is issued one step behind K_j so that K_0 and K_1 go out back to back
           mbar_wait_sleep(v_empty, ((j - 1) & 1) ^ 1u);
           mbar_arrive_expect_tx(v_full, SKV_BYTES);
-          tma_load_2d(sV, &tmQKV, v_full, (H + KVH + g) * 64, row_base + (j - 1) * AT_BC);
+          tma_load_2d(sV, &tmQKV, v_full, (H + KVH + g) * 64, row_base + (j_begin + j - 1) * AT_BC);
         }
       }
-      mbar_wait_sleep(v_empty, ((n_kv - 1) & 1) ^ 1u);
+      mbar_wait_sleep(v_empty, ((n_it - 1) & 1) ^ 1u);
       mbar_arrive_expect_tx(v_full, SKV_BYTES);
-      tma_load_2d(sV, &tmQKV, v_full, (H + KVH + g) * 64, row_base + (n_kv - 1) * AT_BC);
+      tma_load_2d(sV, &tmQKV, v_full, (H + KVH + g) * 64, row_base + (j_begin + n_it - 1) * AT_BC);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -128,8 +134,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       mbar_wait_sleep(k_full, 0);
       tc_fence_after();
       issue_s(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
+      for (int j = 0; j < n_it; ++j) {
+        if (j + 1 < n_it) {
           // S_{j+1} is issued BEFORE P_j is needed: the softmax warps copied S_j to registers (s_empty), so the tensor
           // pipe computes the next scores while they do exp / pack / correction for this tile
           mbar_wait_sleep(k_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
@@ -158,11 +164,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float sl2 = scale * 1.4426950408889634f;
     float m_run = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      const int k0 = j * AT_BC;
+    const int lb = (seg_start && qrow < T) ? seg_start[row_base + qrow] : 0;   // first visible key of this row
+    for (int j = 0; j < n_it; ++j) {
+      const int k0 = (j_begin + j) * AT_BC;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const bool need_mask = (CAUSAL && k0 + AT_BC - 1 > q0) || (k0 + AT_BC > T);
+      const bool need_mask = (CAUSAL && k0 + AT_BC - 1 > q0) || (k0 + AT_BC > T) || (k0 < lb);
       // the whole 128-key row of S lives in registers: ONE pass over TMEM (all four loads in flight, one wait)
       uint32_t v[4][32];
 #pragma unroll
@@ -177,7 +184,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int key = k0 + c * 32 + i;
-            if (key >= T || (CAUSAL && key > qrow)) v[c][i] = 0xff800000u;  // -inf
+            if (key >= T || (CAUSAL && key > qrow) || key < lb) v[c][i] = 0xff800000u;  // -inf
           }
       }
       float mx = m_run;
@@ -239,7 +246,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue
-    mbar_wait(o_done, (n_kv - 1) & 1);
+    mbar_wait(o_done, (n_it - 1) & 1);
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
     bf16* op = o + ((size_t)(row_base + qrow)) * ldo + h * 64;
@@ -275,7 +282,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
 
 // q/k/v: column slices of one [B*T, ld] bf16 buffer starting at `qkv` (q heads first, then KVH k heads, then KVH v heads)
 int sk_attn_tc_fwd_launch(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, int KVH, int ld, int ldo, int causal,
-                          float scale, cudaStream_t s) {
+                          float scale, cudaStream_t s, const int* seg_start) {
+  SK_REQUIRE(seg_start == nullptr || causal, "attn_tc_fwd: document segments need the causal kernel");
   SK_REQUIRE(H % KVH == 0, "attention: H must be a multiple of KVH");
   SK_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "attention: leading dims must be multiples of 8");
   CUtensorMap tm;
@@ -289,8 +297,8 @@ int sk_attn_tc_fwd_launch(const bf16* qkv, bf16* o, float* lse, int B, int T, in
   }
   dim3 grid(H, B, (T + AT_BR - 1) / AT_BR);   // tile index slowest: see the kernel's note on dispatch order
   sk_prof_begin(1, s);
-  if (causal) SK_CUDA_CHECK(sk_launch_pdl(attn_tc_fwd_kernel<true>, dim3(grid), dim3(AT_THREADS), (size_t)(AT_SMEM), s, tm, o, lse, T, ldo, H, KVH, scale));
-  else SK_CUDA_CHECK(sk_launch_pdl(attn_tc_fwd_kernel<false>, dim3(grid), dim3(AT_THREADS), (size_t)(AT_SMEM), s, tm, o, lse, T, ldo, H, KVH, scale));
+  if (causal) SK_CUDA_CHECK(sk_launch_pdl(attn_tc_fwd_kernel<true>, dim3(grid), dim3(AT_THREADS), (size_t)(AT_SMEM), s, tm, o, lse, T, ldo, H, KVH, scale, seg_start));
+  else SK_CUDA_CHECK(sk_launch_pdl(attn_tc_fwd_kernel<false>, dim3(grid), dim3(AT_THREADS), (size_t)(AT_SMEM), s, tm, o, lse, T, ldo, H, KVH, scale, seg_start));
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;
@@ -578,7 +586,8 @@ template <bool CAUSAL>
 __global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                       const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
-                      const float* __restrict__ delta, bf16* __restrict__ dq, int T, int ldg, int H, int KVH, float scale) {
+                      const float* __restrict__ delta, bf16* __restrict__ dq, int T, int ldg, int H, int KVH, float scale,
+                      const int* __restrict__ seg_start) {
   griddep_launch();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -625,21 +634,24 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   const uint32_t tmem_base = *tmem_slot_ptr;
   griddep_wait();   // prologue (barriers, TMEM) may overlap the previous kernel's tail; its outputs are visible from here
   const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdQ = tmem_base + 128;
+  // packed batches: skip key tiles before the first document of this query tile, mask keys before each row's document
+  const int j_begin = seg_start ? seg_start[row_base + q0] / BQ_BC : 0;
+  const int n_it = n_kv - j_begin;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, 2 * SQ_BYTES);
       tma_load_2d(sQ, &tmQKV128, q_full, h * 64, row_base + q0);
       tma_load_2d(sdO, &tmDO, q_full, h * 64, row_base + q0);
-      for (int j = 0; j < n_kv; ++j) {
+      for (int j = 0; j < n_it; ++j) {
         const int st = j & 1;
         const uint32_t par = ((j >> 1) & 1) ^ 1u;
         mbar_wait_sleep(k_empty + 8 * st, par);
         mbar_arrive_expect_tx(k_full + 8 * st, T64_BYTES);
-        tma_load_2d(sK + st * T64_BYTES, &tmQKV64, k_full + 8 * st, (H + g) * 64, row_base + j * BQ_BC);
+        tma_load_2d(sK + st * T64_BYTES, &tmQKV64, k_full + 8 * st, (H + g) * 64, row_base + (j_begin + j) * BQ_BC);
         mbar_wait_sleep(v_empty + 8 * st, par);
         mbar_arrive_expect_tx(v_full + 8 * st, T64_BYTES);
-        tma_load_2d(sV + st * T64_BYTES, &tmQKV64, v_full + 8 * st, (H + KVH + g) * 64, row_base + j * BQ_BC);
+        tma_load_2d(sV + st * T64_BYTES, &tmQKV64, v_full + 8 * st, (H + KVH + g) * 64, row_base + (j_begin + j) * BQ_BC);
       }
     }
   } else if (warp == 1) {
@@ -662,8 +674,8 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       mbar_wait_sleep(v_full, 0);
       tc_fence_after();
       issue_sdp(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
+      for (int j = 0; j < n_it; ++j) {
+        if (j + 1 < n_it) {
           const int st = (j + 1) & 1;
           mbar_wait_sleep(k_full + 8 * st, ((j + 1) >> 1) & 1);
           mbar_wait_sleep(v_full + 8 * st, ((j + 1) >> 1) & 1);
@@ -680,7 +692,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
                      (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(k_empty + 8 * (j & 1));
         tc_commit(ds_empty);
-        if (j == n_kv - 1) tc_commit(dq_done);
+        if (j == n_it - 1) tc_commit(dq_done);
       }
     }
   } else {
@@ -699,8 +711,9 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     const f32x2 nlse2 = dup2(row_ok ? -lse[soff] * 1.4426950408889634f : 0.f);
     const f32x2 del2 = dup2(row_ok ? delta[soff] : 0.f);
     const f32x2 sl22 = dup2(sl2);
-    for (int j = 0; j < n_kv; ++j) {
-      const int k0 = j * BQ_BC;
+    const int lb = (seg_start && row_ok) ? seg_start[row_base + qrow] : 0;   // first visible key of this row
+    for (int j = 0; j < n_it; ++j) {
+      const int k0 = (j_begin + j) * BQ_BC;
       mbar_wait(sdp_full, j & 1);
       tc_fence_after();
       uint32_t sv[32], dv[32];
@@ -710,7 +723,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
-      const bool need_mask = (CAUSAL && k0 + BQ_BC - 1 > q0) || (k0 + BQ_BC > T) || (q0 + AT_BR > T);
+      const bool need_mask = (CAUSAL && k0 + BQ_BC - 1 > q0) || (k0 + BQ_BC > T) || (q0 + AT_BR > T) || (k0 < lb);
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -719,8 +732,8 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
         if (need_mask) {
           const int key = k0 + half * 32 + 2 * i;
-          if (!row_ok || key >= T || (CAUSAL && key > qrow)) p0 = 0.f;
-          if (!row_ok || key + 1 >= T || (CAUSAL && key + 1 > qrow)) p1 = 0.f;
+          if (!row_ok || key >= T || (CAUSAL && key > qrow) || key < lb) p0 = 0.f;
+          if (!row_ok || key + 1 >= T || (CAUSAL && key + 1 > qrow) || key + 1 < lb) p1 = 0.f;
         }
         float d0, d1;
         upk2(mul2(pk2(p0, p1), sub2(pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), del2)), d0, d1);
@@ -768,32 +781,35 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
 }
 
 constexpr int BK_BR = 64;                                   // query rows per step in the dK/dV kernel
-constexpr uint32_t DKDV_SMEM = 2 * SKV_BYTES + 4 * T64_BYTES + 2 * SKV_BYTES + 2 * 2 * 64 * 4 + 256 + 1024;
+constexpr uint32_t DKDV_SMEM = 2 * SKV_BYTES + 4 * T64_BYTES + 2 * SKV_BYTES + 2 * 3 * 64 * 4 + 256 + 1024;
 
 template <bool CAUSAL>
 __global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                         const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
                         const float* __restrict__ delta, float* __restrict__ partial /*[B][H][T][128]*/, int T, int H,
-                        int KVH, float scale) {
+                        int KVH, float scale, const int* __restrict__ seg_start, const int* __restrict__ seg_end) {
   griddep_launch();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = smem_base, sV = sK + SKV_BYTES, sQ = sV + SKV_BYTES /*[2]*/, sdO = sQ + 2 * T64_BYTES /*[2]*/,
-                 sPT = sdO + 2 * T64_BYTES, sdST = sPT + SKV_BYTES, sStat = sdST + SKV_BYTES, bar = sStat + 2 * 2 * 64 * 4;
+                 sPT = sdO + 2 * T64_BYTES, sdST = sPT + SKV_BYTES, sStat = sdST + SKV_BYTES, bar = sStat + 2 * 3 * 64 * 4;
   const uint32_t kv_full = bar, q_full = bar + 8, q_empty = bar + 24, sdp_full = bar + 40, sdp_empty = bar + 48,
                  pds_full = bar + 56, pds_empty = bar + 64, acc_done = bar + 72, tmem_slot = bar + 80;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* stat_ptr = reinterpret_cast<float*>(smem_raw + (sStat - smem_u32(smem_raw)));   // [stage][lse|delta][64]
+  float* stat_ptr = reinterpret_cast<float*>(smem_raw + (sStat - smem_u32(smem_raw)));   // [stage][lse|delta|seg][64]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.z;                   // key tile 0 has the most query tiles under the causal mask; tile index
   const int h = blockIdx.x, b = blockIdx.y;    // slowest so the heavy tiles of every (head, batch) are dispatched first
   const int g = h / (H / KVH);
   const int k0 = kt * AT_BC;
   const int row_base = b * T;
-  const int n_qt = (T + BK_BR - 1) / BK_BR;
+  int n_qt = (T + BK_BR - 1) / BK_BR;
+  // packed batches: queries of later documents never see these keys -- stop at the end of the document of the tile's
+  // last key (seg_end[token] = in-row index one past its document)
+  if (seg_end) n_qt = min(n_qt, (seg_end[row_base + min(k0 + AT_BC, T) - 1] + BK_BR - 1) / BK_BR);
   const int qt_begin = CAUSAL ? (k0 / BK_BR) : 0;
-  const int n_it = n_qt - qt_begin;
+  const int n_it = max(0, n_qt - qt_begin);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV128);
@@ -891,16 +907,17 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     // latency is off the per-iteration critical path.
     auto fetch_stat = [&](int it) -> float {
       const int qq = (qt_begin + it) * BK_BR + (tid & 63);
+      if (tid >= 128) return __int_as_float((seg_start && qq < T) ? seg_start[row_base + qq] : 0);   // [128,192): seg_start
       const size_t off = ((size_t)b * H + h) * T + (qq < T ? qq : 0);
       return qq < T ? ((tid < 64) ? -lse[off] * 1.4426950408889634f : delta[off]) : 0.f;
     };
-    if (n_it > 0 && tid < 128) stat_ptr[tid] = fetch_stat(0);
+    if (n_it > 0 && tid < 192) stat_ptr[tid] = fetch_stat(0);
     asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int i = 0; i < n_it; ++i) {
       const int q0 = (qt_begin + i) * BK_BR;
-      const float* st_lse = stat_ptr + (i & 1) * 128;
+      const float* st_lse = stat_ptr + (i & 1) * 192;
       float stat_next = 0.f;
-      if (i + 1 < n_it && tid < 128) stat_next = fetch_stat(i + 1);
+      if (i + 1 < n_it && tid < 192) stat_next = fetch_stat(i + 1);
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
       uint32_t sv[32], dv[32];
@@ -910,7 +927,7 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
-      const bool need_mask = (CAUSAL && q0 < k0 + AT_BC) || (q0 + BK_BR > T) || (k0 + AT_BC > T);
+      const bool need_mask = (CAUSAL && q0 < k0 + AT_BC) || (q0 + BK_BR > T) || (k0 + AT_BC > T) || seg_start != nullptr;
       uint32_t pp[16], pd[16];
       // packed-pair math (two queries per instruction); dS'^T omits the 1/sqrt(d) factor, applied to dK in the epilogue
 #pragma unroll
@@ -923,8 +940,9 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
         float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
         if (need_mask) {
           const int qrow = q0 + qi;
-          if (key >= T || qrow >= T || (CAUSAL && key > qrow)) p0 = 0.f;
-          if (key >= T || qrow + 1 >= T || (CAUSAL && key > qrow + 1)) p1 = 0.f;
+          const int2 sg = *reinterpret_cast<const int2*>(st_lse + 128 + qi);     // first visible key of the two queries
+          if (key >= T || qrow >= T || (CAUSAL && key > qrow) || key < sg.x) p0 = 0.f;
+          if (key >= T || qrow + 1 >= T || (CAUSAL && key > qrow + 1) || key < sg.y) p1 = 0.f;
         }
         pp[e] = pack_bf16(p0, p1);
         float d0, d1;
@@ -945,7 +963,7 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
       if (i + 1 < n_it) {
-        if (tid < 128) stat_ptr[((i + 1) & 1) * 128 + tid] = stat_next;
+        if (tid < 192) stat_ptr[((i + 1) & 1) * 192 + tid] = stat_next;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
@@ -1016,7 +1034,9 @@ __global__ void attn_tc_group_reduce_kernel(const float* __restrict__ partial, b
 int sk_attn_delta_launch(const bf16* o, const bf16* d_o, float* delta, int B, int T, int H, int ldo, cudaStream_t s);
 int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse, float* delta, float* partial,
                           bf16* dqkv, int B, int T, int H, int KVH, int ld, int ldo, int ldg, int causal, float scale,
-                          cudaStream_t s) {
+                          cudaStream_t s, const int* seg_start, const int* seg_end) {
+  SK_REQUIRE((seg_start == nullptr) == (seg_end == nullptr), "attn_tc_bwd: seg_start and seg_end go together");
+  SK_REQUIRE(seg_start == nullptr || causal, "attn_tc_bwd: document segments need the causal kernels");
   SK_REQUIRE(H % KVH == 0, "attention: H must be a multiple of KVH");
   CUtensorMap tm128, tm64, tmdo128, tmdo64;
   int rc;
@@ -1039,11 +1059,11 @@ int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const
   bf16* dk = dqkv + H * 64;
   bf16* dv = dqkv + (H + KVH) * 64;
   if (causal) {
-    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dkdv_kernel<true>, dim3(g1), dim3(BWD_THREADS), (size_t)(DKDV_SMEM), s, tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale));
-    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dq_kernel<true>, dim3(g2), dim3(BWD_THREADS), (size_t)(DQ_SMEM), s, tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale));
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dkdv_kernel<true>, dim3(g1), dim3(BWD_THREADS), (size_t)(DKDV_SMEM), s, tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale, seg_start, seg_end));
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dq_kernel<true>, dim3(g2), dim3(BWD_THREADS), (size_t)(DQ_SMEM), s, tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale, seg_start));
   } else {
-    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dkdv_kernel<false>, dim3(g1), dim3(BWD_THREADS), (size_t)(DKDV_SMEM), s, tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale));
-    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dq_kernel<false>, dim3(g2), dim3(BWD_THREADS), (size_t)(DQ_SMEM), s, tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale));
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dkdv_kernel<false>, dim3(g1), dim3(BWD_THREADS), (size_t)(DKDV_SMEM), s, tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale, seg_start, seg_end));
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dq_kernel<false>, dim3(g2), dim3(BWD_THREADS), (size_t)(DQ_SMEM), s, tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale, seg_start));
   }
   sk_count_launch();
   sk_count_launch();                               // two kernels above; the reduce below is counted by SK_LAUNCH_CHECK

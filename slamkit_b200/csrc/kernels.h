@@ -63,6 +63,7 @@ int sk_gradnorm_launch(const bf16* g, const long* chunk_start, const int* chunk_
 int sk_adamw_launch(bf16* p, const bf16* g, bf16* m, bf16* v, long n, float lr, float beta1, float beta2, float eps,
                     float wd, int step, const float* clip_stats, cudaStream_t s);
 int sk_transpose_launch(const bf16* in, bf16* out, int M, int N, cudaStream_t s);
+int sk_seg_bounds_launch(const int32_t* pos_ids, int32_t* seg_start, int32_t* seg_end, int B, int T, cudaStream_t s);
 
 // attention.cu
 int sk_attn_fwd_launch(const bf16* q, const bf16* k, const bf16* v, bf16* o, float* lse, int B, int T, int H, int KVH,
@@ -77,11 +78,13 @@ int sk_attn_fwd_split_launch(const bf16* q_hi, const bf16* q_lo, const bf16* k_h
 // attention_tc.cu (tcgen05 / TMEM flash attention)
 int sk_attn_tc_fwd_split_launch(const bf16* qkv_hi, const bf16* qkv_lo, bf16* o_hi, bf16* o_lo, int B, int T, int H, int ld,
                                 int ldo, float scale, cudaStream_t s);
+// seg_start / seg_end (optional, int32 [B*T]): in-row index of the first token of each token's document and one past
+// its last -- block-diagonal causal attention for packed batches (sk_seg_bounds_launch builds them from position_ids)
 int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse, float* delta, float* partial,
                           bf16* dqkv, int B, int T, int H, int KVH, int ld, int ldo, int ldg, int causal, float scale,
-                          cudaStream_t s);
+                          cudaStream_t s, const int* seg_start = nullptr, const int* seg_end = nullptr);
 int sk_attn_tc_fwd_launch(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, int KVH, int ld, int ldo, int causal,
-                          float scale, cudaStream_t s);
+                          float scale, cudaStream_t s, const int* seg_start = nullptr);
 
 // hubert_kernels.cu
 int sk_split_f32_launch(const float* x, bf16* hi, bf16* lo, long n, cudaStream_t s);

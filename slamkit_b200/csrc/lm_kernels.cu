@@ -646,6 +646,47 @@ __global__ void transpose_kernel(const bf16* __restrict__ in, bf16* __restrict__
     if (x < M && y + j < N) out[(size_t)(y + j) * M + x] = tile[threadIdx.x][threadIdx.y + j];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed batches: a document starts wherever position_ids == 0 (and at column 0).  seg_start[t] = index of the last
+// start <= t, seg_end[t] = index of the first start > t (or T).  One block per batch row; threads own contiguous
+// chunks, chunk summaries are combined serially (T <= a few thousand: this is a ~3 us kernel).
+// Reference: HF derives cu_seqlens for its varlen flash-attention path the same way (HF:modeling_flash_attention_utils.py
+// prepare_fa_kwargs_from_position_ids: boundaries at position_ids == 0), used by DataCollatorWithFlattening batches
+// (slamkit/data/hf_dataset.py:61-62).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+seg_bounds_kernel(const int32_t* __restrict__ pos, int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_end, int T) {
+  __shared__ int s_last[256], s_first[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int per = (T + 255) / 256;
+  const int t0 = min(T, tid * per), t1 = min(T, t0 + per);
+  const int32_t* p = pos + (size_t)b * T;
+  int last = -1, first = T;                      // last / first document start inside this thread's chunk
+  for (int t = t0; t < t1; ++t) {
+    if (t == 0 || p[t] == 0) {
+      last = t;
+      if (first == T) first = t;
+    }
+  }
+  s_last[tid] = last;
+  s_first[tid] = first;
+  __syncthreads();
+  int carry_last = 0;                            // last start before this chunk
+  for (int i = 0; i < tid; ++i) carry_last = s_last[i] >= 0 ? s_last[i] : carry_last;
+  int carry_first = T;                           // first start after this chunk
+  for (int i = 255; i > tid; --i) carry_first = s_first[i] < T ? s_first[i] : carry_first;
+  int cur = carry_last;
+  for (int t = t0; t < t1; ++t) {
+    if (t == 0 || p[t] == 0) cur = t;
+    seg_start[(size_t)b * T + t] = cur;
+  }
+  int nxt = carry_first;
+  for (int t = t1 - 1; t >= t0; --t) {
+    seg_end[(size_t)b * T + t] = nxt;
+    if (t == 0 || p[t] == 0) nxt = t;
+  }
+}
+
 inline int grid_for(long work_items, int threads, int max_blocks_per_sm = 16) {
   long b = (work_items + threads - 1) / threads;
   long cap = (long)sk_num_sms() * max_blocks_per_sm;
@@ -762,6 +803,12 @@ int sk_adamw_launch(bf16* p, const bf16* g, bf16* m, bf16* v, long n, float lr, 
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   adamw_kernel<<<grid_for(n / 8, 256, 8), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, clip_stats);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_seg_bounds_launch(const int32_t* pos_ids, int32_t* seg_start, int32_t* seg_end, int B, int T, cudaStream_t s) {
+  SK_REQUIRE(pos_ids && seg_start && seg_end && B > 0 && T > 0, "seg_bounds: bad arguments");
+  seg_bounds_kernel<<<B, 256, 0, s>>>(pos_ids, seg_start, seg_end, T);
   SK_LAUNCH_CHECK();
   return 0;
 }

@@ -29,7 +29,7 @@ struct WsLayout {
   int64_t X, h1, rstd1, qkv, ao, lse, xmid, h2, rstd2, gu, act;  // per-layer strides below
   int64_t sX, sh, srstd, sqkv, slse, sgu, sact;
   int64_t hf, rstdf, logits, dlogits, dxA, dxB, dh, dao, dqkv, dact, dgu, delta;
-  int64_t dw_partial, colsum_partial, ce_partial, embed_scratch, splitk, splitk_bytes, attn_partial, total;
+  int64_t dw_partial, colsum_partial, ce_partial, embed_scratch, splitk, splitk_bytes, attn_partial, seg_start, seg_end, total;
 };
 }  // namespace
 
@@ -118,6 +118,8 @@ WsLayout make_layout(const SkLm* lm, int B, int T) {
   w.ce_partial = take((int64_t)sk_ce_blocks((int)M) * 2 * 4);
   w.embed_scratch = take((int64_t)lm->Vp * lm->d * 4);
   w.attn_partial = take((int64_t)B * lm->H * T * 128 * 4);   // per-head fp32 dK|dV partials (tcgen05 backward)
+  w.seg_start = take(M * 4);   // document bounds of packed batches (position_ids given), int32 per token
+  w.seg_end = take(M * 4);
   w.total = cur;
   return w;
 }
@@ -168,6 +170,14 @@ int forward_impl(SkLm* lm, const int64_t* ids, const int64_t* labels, const int3
   bf16* X0 = wsp<bf16>(lm, w.X);
   SK_TRY(sk_embed_fwd_launch(ids, P + lm->off_embed, X0, M, d, lm->V, s));
   const float scale = 1.0f / sqrtf((float)lm->hd);
+  // packed batch (position_ids given): document bounds -> block-diagonal causal attention, as the reference's varlen
+  // flash-attention path does (slamkit/data/hf_dataset.py:61-62 + HF prepare_fa_kwargs_from_position_ids)
+  const int* seg_start = nullptr;
+  if (pos_ids) {
+    SK_REQUIRE(lm->attn_tc >= 2, "sk_lm: position_ids (packed batches) need the tcgen05 attention kernels (SK_ATTN_TC=2)");
+    SK_TRY(sk_seg_bounds_launch(pos_ids, wsp<int32_t>(lm, w.seg_start), wsp<int32_t>(lm, w.seg_end), B, T, s));
+    seg_start = wsp<int32_t>(lm, w.seg_start);
+  }
   for (int l = 0; l < L; ++l) {
     const LayerOff& o = lm->lo[l];
     bf16* x = wsp<bf16>(lm, w.X + w.sX * l);
@@ -187,7 +197,7 @@ int forward_impl(SkLm* lm, const int64_t* ids, const int64_t* labels, const int3
     SK_TRY(linear_fwd(M, lm->qkv_dim, d, h1, P + o.wqkv, qkv, lm->cfg.qkv_bias ? P + o.bqkv : nullptr, nullptr, s));
     SK_TRY(sk_rope_launch(qkv, lm->rope_cos, lm->rope_sin, pos_ids, M, T, lm->qkv_dim, lm->H + lm->KVH, lm->hd, 0, s));
     if (lm->attn_tc)
-      SK_TRY(sk_attn_tc_fwd_launch(qkv, ao, lse, B, T, lm->H, lm->KVH, lm->qkv_dim, d, 1, scale, s));
+      SK_TRY(sk_attn_tc_fwd_launch(qkv, ao, lse, B, T, lm->H, lm->KVH, lm->qkv_dim, d, 1, scale, s, seg_start));
     else
       SK_TRY(sk_attn_fwd_launch(qkv, qkv + lm->H * lm->hd, qkv + (lm->H + lm->KVH) * lm->hd, ao, lse, B, T, lm->H,
                                 lm->KVH, lm->qkv_dim, d, 1, scale, s));
@@ -260,7 +270,8 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
     SK_TRY(linear_wgrad(M, d, d, dxB, ao, G + o.wo, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
     if (lm->attn_tc >= 2)
       SK_TRY(sk_attn_tc_bwd_launch(qkv, ao, dao, lse, wsp<float>(lm, w.delta), wsp<float>(lm, w.attn_partial), dqkv, B, T,
-                                   lm->H, lm->KVH, Q, d, Q, 1, scale, s));
+                                   lm->H, lm->KVH, Q, d, Q, 1, scale, s, pos_ids ? wsp<int32_t>(lm, w.seg_start) : nullptr,
+                                   pos_ids ? wsp<int32_t>(lm, w.seg_end) : nullptr));
     else
       SK_TRY(sk_attn_bwd_launch(qkv, qkv + lm->H * lm->hd, qkv + (lm->H + lm->KVH) * lm->hd, ao, dao, lse,
                                 wsp<float>(lm, w.delta), dqkv, dqkv + lm->H * lm->hd, dqkv + (lm->H + lm->KVH) * lm->hd,

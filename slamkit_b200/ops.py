@@ -166,17 +166,31 @@ def attn_fwd(qkv: torch.Tensor, B: int, T: int, H: int, KVH: int, causal: bool, 
     return o, lse
 
 
-def attn_tc_fwd(qkv: torch.Tensor, B: int, T: int, H: int, KVH: int, causal: bool, scale: float):
-    """tcgen05 flash-attention forward (sk_attn_tc_fwd); same contract as attn_fwd."""
+def seg_bounds(pos_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Document bounds of a packed batch from position_ids [B, T] (sk_seg_bounds): (seg_start, seg_end) int32 [B*T]."""
+    lib = L.require_cuda()
+    B, T = pos_ids.shape
+    pos = pos_ids.to(torch.int32).contiguous()
+    ss = torch.empty(B * T, device=pos.device, dtype=torch.int32)
+    se = torch.empty(B * T, device=pos.device, dtype=torch.int32)
+    L.check(lib.sk_seg_bounds(L.ptr(pos), L.ptr(ss), L.ptr(se), B, T, L.stream_ptr()))
+    return ss, se
+
+
+def attn_tc_fwd(qkv: torch.Tensor, B: int, T: int, H: int, KVH: int, causal: bool, scale: float,
+                seg_start: Optional[torch.Tensor] = None):
+    """tcgen05 flash-attention forward (sk_attn_tc_fwd); same contract as attn_fwd.  seg_start (from seg_bounds) makes
+    it block-diagonal causal for packed batches."""
     lib = L.require_cuda()
     o = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.bfloat16)
     lse = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
     L.check(lib.sk_attn_tc_fwd(L.ptr(qkv), L.ptr(o), L.ptr(lse), B, T, H, KVH, qkv.stride(0), o.stride(0), int(causal),
-                               L.f32(scale), L.stream_ptr()))
+                               L.f32(scale), L.ptr(seg_start), L.stream_ptr()))
     return o, lse
 
 
-def attn_tc_bwd(qkv, o, d_o, lse, B, T, H, KVH, causal: bool, scale: float) -> torch.Tensor:
+def attn_tc_bwd(qkv, o, d_o, lse, B, T, H, KVH, causal: bool, scale: float, seg_start: Optional[torch.Tensor] = None,
+                seg_end: Optional[torch.Tensor] = None) -> torch.Tensor:
     """tcgen05 flash-attention backward (sk_attn_tc_bwd); same contract as attn_bwd."""
     lib = L.require_cuda()
     dqkv = torch.empty_like(qkv)
@@ -184,7 +198,7 @@ def attn_tc_bwd(qkv, o, d_o, lse, B, T, H, KVH, causal: bool, scale: float) -> t
     partial = torch.empty((B, H, T, 128), device=qkv.device, dtype=torch.float32)
     L.check(lib.sk_attn_tc_bwd(L.ptr(qkv), L.ptr(o), L.ptr(d_o), L.ptr(lse), L.ptr(delta), L.ptr(partial), L.ptr(dqkv),
                                B, T, H, KVH, qkv.stride(0), o.stride(0), dqkv.stride(0), int(causal), L.f32(scale),
-                               L.stream_ptr()))
+                               L.ptr(seg_start), L.ptr(seg_end), L.stream_ptr()))
     return dqkv
 
 

@@ -317,6 +317,78 @@ def test_attention_tc_bwd(B, T, H, KVH, causal):
     assert rel_err(dqkv[:, nk:], dqkv_ref[:, nk:]) < 1e-2, ("dv", rel_err(dqkv[:, nk:], dqkv_ref[:, nk:]))
 
 
+def _packed_positions(B, T, seed):
+    """position_ids of a packed batch: documents of random length (some length 1, some tile-aligned) until T is full."""
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.zeros(B, T, dtype=torch.int64)
+    for b in range(B):
+        t = 0
+        while t < T:
+            n = int(torch.randint(1, 300, (1,), generator=g))
+            if int(torch.randint(0, 4, (1,), generator=g)) == 0:
+                n = 128 * int(torch.randint(1, 3, (1,), generator=g))      # a document that ends on a tile boundary
+            n = min(n, T - t)
+            pos[b, t:t + n] = torch.arange(n)
+            t += n
+    return pos
+
+
+def test_seg_bounds_from_position_ids():
+    from slamkit_b200 import ops
+    pos = _packed_positions(3, 1000, seed=3)
+    ss, se = ops.seg_bounds(pos.to(DEV))
+    ss, se = ss.cpu().view(3, 1000), se.cpu().view(3, 1000)
+    for b in range(3):
+        starts = [t for t in range(1000) if t == 0 or pos[b, t] == 0] + [1000]
+        want_s = torch.empty(1000, dtype=torch.int32); want_e = torch.empty(1000, dtype=torch.int32)
+        for a, e in zip(starts[:-1], starts[1:]):
+            want_s[a:e] = a; want_e[a:e] = e
+        assert torch.equal(ss[b], want_s) and torch.equal(se[b], want_e)
+
+
+@pytest.mark.parametrize("B,T,H,KVH", [(2, 640, 4, 2), (1, 1024, 14, 2), (2, 333, 2, 1)])
+def test_attention_tc_packed_documents(B, T, H, KVH):
+    """Packed batches: attention is causal inside a document and empty across documents (what the reference's varlen
+    flash-attention path computes from position_ids).  fp32 reference with the explicit block-diagonal mask."""
+    from slamkit_b200 import ops
+    from oracle.lm_oracle import packed_mask
+    hd = 64
+    qkv = _randn(B * T, (H + 2 * KVH) * hd, seed=9)
+    d_o = _randn(B * T, H * hd, seed=10)
+    scale = 1.0 / math.sqrt(hd)
+    pos = _packed_positions(B, T, seed=11)
+    mask = packed_mask(pos)                                    # [B,1,T,T] bool
+    x = qkv.float().requires_grad_(True)
+    q = x[:, :H * hd].view(B, T, H, hd).transpose(1, 2)
+    k = x[:, H * hd:(H + KVH) * hd].view(B, T, KVH, hd).transpose(1, 2)
+    v = x[:, (H + KVH) * hd:].view(B, T, KVH, hd).transpose(1, 2)
+    rep = H // KVH
+    k = k[:, :, None].expand(-1, -1, rep, -1, -1).reshape(B, H, T, hd)
+    v = v[:, :, None].expand(-1, -1, rep, -1, -1).reshape(B, H, T, hd)
+    sc = ((q @ k.transpose(-1, -2)) * scale).masked_fill(~mask, float("-inf"))
+    o_ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * T, H * hd)
+    lse_ref = torch.logsumexp(sc, -1).detach()
+    (o_ref * d_o.float()).sum().backward()
+    ss, se = ops.seg_bounds(pos.to(DEV))
+    o, lse = ops.attn_tc_fwd(qkv.to(DEV), B, T, H, KVH, True, scale, seg_start=ss)
+    assert rel_err(o.cpu(), o_ref.detach()) < 5e-3, rel_err(o.cpu(), o_ref.detach())
+    assert max_abs(lse.cpu(), lse_ref) < 2e-3
+    dqkv = ops.attn_tc_bwd(qkv.to(DEV), o, d_o.to(DEV), lse, B, T, H, KVH, True, scale, seg_start=ss, seg_end=se)
+    dqkv2 = ops.attn_tc_bwd(qkv.to(DEV), o, d_o.to(DEV), lse, B, T, H, KVH, True, scale, seg_start=ss, seg_end=se)
+    assert torch.equal(dqkv, dqkv2)
+    dqkv = dqkv.cpu()
+    nq, nk = H * hd, (H + KVH) * hd
+    assert rel_err(dqkv[:, :nq], x.grad[:, :nq]) < 1e-2, ("dq", rel_err(dqkv[:, :nq], x.grad[:, :nq]))
+    assert rel_err(dqkv[:, nq:nk], x.grad[:, nq:nk]) < 1e-2, ("dk", rel_err(dqkv[:, nq:nk], x.grad[:, nq:nk]))
+    assert rel_err(dqkv[:, nk:], x.grad[:, nk:]) < 1e-2, ("dv", rel_err(dqkv[:, nk:], x.grad[:, nk:]))
+    # one document per row == the plain causal kernel, bit for bit
+    pos1 = torch.arange(T)[None].expand(B, -1).contiguous()
+    s1, e1 = ops.seg_bounds(pos1.to(DEV))
+    o1, lse1 = ops.attn_tc_fwd(qkv.to(DEV), B, T, H, KVH, True, scale, seg_start=s1)
+    o0, lse0 = ops.attn_tc_fwd(qkv.to(DEV), B, T, H, KVH, True, scale)
+    assert torch.equal(o1, o0) and torch.equal(lse1, lse0)
+
+
 # ---------------------------------------------------------------------------------------------- optimiser
 def test_adamw_matches_oracle_and_torch():
     from slamkit_b200 import ops

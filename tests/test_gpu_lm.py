@@ -164,6 +164,48 @@ def test_lm_full_size_properties():
     assert float(m.forward_backward(ids, labels, num_items_in_batch=8192.0).loss) < loss0 - 0.05
 
 
+def test_lm_packed_batch_equals_separate_documents():
+    """Packing (DataCollatorWithFlattening: one row, position_ids restarting per document): logits and loss of the
+    packed row equal those of the documents run one by one, and match the oracle's block-diagonal restatement."""
+    from oracle import lm_oracle as O
+    cfg_o = O.OracleLMConfig(vocab_size=502, hidden=128, n_layers=2, n_heads=2, n_kv_heads=1, head_dim=64, ffn=256)
+    m, p = _mk(cfg_o, 5, 2, 512)
+    g = torch.Generator().manual_seed(3)
+    lens = [37, 128, 1, 200, 90]
+    docs = [torch.randint(2, 502, (n,), generator=g) for n in lens]
+    ids = torch.cat(docs)[None]                                             # [1, 456]
+    pos = torch.cat([torch.arange(n) for n in lens])[None]
+    labels = ids.clone()
+    for a in np.cumsum([0] + lens[:-1]):
+        labels[0, a] = -100                                                 # separator: first token of each document
+    n_items = float((labels[:, 1:] != -100).sum())
+    out = m.forward_backward(ids, labels, position_ids=pos, num_items_in_batch=n_items)
+    loss_packed = float(out.loss)
+    grads_packed = m.grads.clone()
+    lg_packed = m.forward(ids, position_ids=pos).logits[0].float().cpu()
+    # (1) the documents one by one (plain causal kernels)
+    off, nll = 0, 0.0
+    for n, d in zip(lens, docs):
+        if n > 1:
+            lg = m.forward(d[None]).logits[0].float().cpu()
+            assert rel_err(lg_packed[off:off + n], lg) < 8e-3, (n, rel_err(lg_packed[off:off + n], lg))
+            nll += float(torch.nn.functional.cross_entropy(lg[:-1], d[1:], reduction="sum"))
+        off += n
+    assert abs(loss_packed - nll / n_items) < 2e-3 * abs(nll / n_items), (loss_packed, nll / n_items)
+    # (2) the oracle with the explicit block-diagonal mask
+    lo, _, go = O.forward_backward(p, cfg_o, ids, labels, n_items, position_ids=pos, packed=True)
+    assert abs(loss_packed - float(lo)) < 1e-3 * abs(float(lo)), (loss_packed, float(lo))
+    got = m.state_dict_hf(grads=True) if hasattr(m, "state_dict_hf") else None
+    if got is not None:
+        for k in ("lm.model.layers.0.mlp.down_proj.weight", "lm.model.layers.1.self_attn.q_proj.weight",
+                  "lm.model.layers.0.self_attn.v_proj.weight"):
+            assert rel_err(got[k].float().cpu(), go[k].float()) < 3e-2, (k, rel_err(got[k].float().cpu(), go[k].float()))
+    # (3) without position_ids the same row is one long document: different logits after the first boundary
+    lg_plain = m.forward(ids).logits[0].float().cpu()
+    assert rel_err(lg_plain[:lens[0]], lg_packed[:lens[0]]) < 1e-6 and rel_err(lg_plain[lens[0]:], lg_packed[lens[0]:]) > 1e-2
+    assert torch.isfinite(grads_packed.float()).all()
+
+
 def test_grad_norm_and_clip_matches_torch():
     from oracle import lm_oracle as O
     from slamkit_b200.lm import B200AdamW

@@ -83,3 +83,26 @@ def test_cosine_with_min_lr_matches_hf():
         want = 1e-3 * sch.lr_lambdas[0](s)
         got = O.cosine_with_min_lr(s, base_lr=1e-3, min_lr=5e-5, warmup_steps=100, total_steps=1000)
         assert abs(want - got) < 1e-12
+
+
+def test_packed_mask_equals_running_documents_separately():
+    """The oracle's restatement of the reference's packing path (DataCollatorWithFlattening + varlen flash attention,
+    slamkit/data/hf_dataset.py:61-62): a packed row with per-document position_ids gives each document exactly the
+    logits it gets on its own (fp32 so that the comparison is not blurred by bf16 summation order)."""
+    cfg = O.OracleLMConfig(vocab_size=64, hidden=64, n_layers=2, n_heads=2, n_kv_heads=1, head_dim=32, ffn=128)
+    p = {k: v.float() for k, v in O.init_params(cfg, seed=0).items()}
+    g = torch.Generator().manual_seed(0)
+    lens = [5, 1, 17, 9]
+    docs = [torch.randint(2, 64, (n,), generator=g) for n in lens]
+    ids = torch.cat(docs)[None]
+    pos = torch.cat([torch.arange(n) for n in lens])[None]
+    doc = O.document_ids(pos.clone())
+    assert doc.tolist() == [sum(([i + 1] * n for i, n in enumerate(lens)), [])]
+    packed = O.forward_logits(p, cfg, ids, pos, packed=True)[0]
+    off = 0
+    for n, d in zip(lens, docs):
+        alone = O.forward_logits(p, cfg, d[None])[0]
+        assert float((packed[off:off + n] - alone).abs().max()) < 1e-4
+        off += n
+    leaky = O.forward_logits(p, cfg, ids, pos, packed=False)[0]       # same row without the document mask
+    assert float((leaky[lens[0]:] - packed[lens[0]:]).abs().max()) > 1e-3
