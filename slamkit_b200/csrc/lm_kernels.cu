@@ -487,6 +487,96 @@ ce_fwd_bwd_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ l
   }
 }
 
+// Large-vocabulary variant (interleaved text+unit vocabularies, ~152 k columns: SURVEY.md f-1): one block per row, an
+// online (max, sum) pass over the row, then a second pass that writes the gradient -- logits are read twice and the
+// gradient written once (3 x M x V x 2 B; 7.5 GB at [8192, 152 k]).  Same outputs and rounding as the warp-per-row kernel.
+__global__ void __launch_bounds__(256)
+ce_large_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ labels, bf16* __restrict__ dlogits,
+                float* __restrict__ partial /*[M][2]*/, float* __restrict__ row_nll, const float* __restrict__ row_weight,
+                int M, int T, int V, int ldl, float grad_scale) {
+  __shared__ float s_m[8], s_s[8];
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = row % T;
+  long target = -100;
+  if (t < T - 1) target = labels[row + 1];
+  const bool valid = (target >= 0 && target < V);
+  const bf16* lrow = logits + (size_t)row * ldl;
+  const int nvec = ldl / 8;
+  float m = -INFINITY, sum = 0.f;
+  for (int c = threadIdx.x; c < nvec; c += 256) {
+    const uint4 lv = ldg128_stream(lrow + c * 8);
+    const uint32_t u[4] = {lv.x, lv.y, lv.z, lv.w};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(u[k]);
+      v[2 * k] = (c * 8 + 2 * k < V) ? f.x : -INFINITY;
+      v[2 * k + 1] = (c * 8 + 2 * k + 1 < V) ? f.y : -INFINITY;
+    }
+    float cm = v[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) cm = fmaxf(cm, v[k]);
+    if (cm > -INFINITY) {
+      const float mn = fmaxf(m, cm);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += ex2_approx((v[k] - mn) * 1.4426950408889634f);
+      sum = sum * ex2_approx((m - mn) * 1.4426950408889634f) + acc;   // m == -inf: sum is 0 and 0 * 0 = 0
+      m = mn;
+    }
+  }
+  // combine (m, sum) pairs: warp, then block
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mn = fmaxf(m, m2);
+    if (mn > -INFINITY) sum = sum * ex2_approx((m - mn) * 1.4426950408889634f) + s2 * ex2_approx((m2 - mn) * 1.4426950408889634f);
+    m = mn;
+  }
+  if (lane == 0) { s_m[warp] = m; s_s[warp] = sum; }
+  __syncthreads();
+  m = s_m[0]; sum = s_s[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) {
+    const float mn = fmaxf(m, s_m[i]);
+    if (mn > -INFINITY) sum = sum * ex2_approx((m - mn) * 1.4426950408889634f) + s_s[i] * ex2_approx((s_m[i] - mn) * 1.4426950408889634f);
+    m = mn;
+  }
+  const float lse = m + logf(sum);
+  const float tgt_logit = valid ? __bfloat162float(lrow[target]) : 0.f;
+  if (threadIdx.x == 0) {
+    partial[2 * row] = valid ? (lse - tgt_logit) : 0.f;
+    partial[2 * row + 1] = valid ? 1.f : 0.f;
+    if (row_nll) row_nll[row] = valid ? (lse - tgt_logit) : 0.f;
+  }
+  if (dlogits) {
+    const float gs = row_weight ? grad_scale * row_weight[row] : grad_scale;
+    const float nlse2 = -lse * 1.4426950408889634f;
+    bf16* drow = dlogits + (size_t)row * ldl;
+    for (int c = threadIdx.x; c < nvec; c += 256) {
+      float o[8];
+      if (valid) {
+        const uint4 lv = ldg128_stream(lrow + c * 8);
+        const uint32_t u[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16(u[k]);
+          o[2 * k] = (c * 8 + 2 * k < V) ? ex2_approx(fmaf(f.x, 1.4426950408889634f, nlse2)) : 0.f;
+          o[2 * k + 1] = (c * 8 + 2 * k + 1 < V) ? ex2_approx(fmaf(f.y, 1.4426950408889634f, nlse2)) : 0.f;
+        }
+        const int d = (int)target - c * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (o[k] - (k == d ? 1.f : 0.f)) * gs;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+      }
+      stg128(drow + c * 8, make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7])));
+    }
+  }
+}
+
 // out[0] = loss (sum/denom), out[1] = n_valid, out[2] = raw nll sum.   denom<=0 -> mean over valid tokens.
 __global__ void ce_finalize_kernel(const float* __restrict__ partial, int nblocks, float denom, float* __restrict__ out) {
   __shared__ double sa[256], sb[256];
@@ -768,16 +858,24 @@ int sk_swiglu_bwd_launch(const bf16* gu, const bf16* dact, bf16* dgu, int M, int
   SK_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int sk_ce_blocks(int M) { return (M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; }
+// partial[] entries sk_ce_launch may write: one pair per row in the large-vocabulary kernel (a superset of the per-block
+// pairs of the small one)
+extern "C" int sk_ce_blocks(int M) { return M; }
 // stats_out: float[3] = {loss, n_valid, nll_sum}.  num_items > 0: loss = sum/num_items (reference 'sum' path);
 // num_items <= 0: mean over valid tokens.  dloss scales the gradient.
 int sk_ce_launch(const bf16* logits, const int64_t* labels, bf16* dlogits, float* partial, float* row_nll,
                  float* stats_out, int M, int T, int V, int ldl, float num_items, float dloss, cudaStream_t s,
                  const float* row_weight) {
-  SK_REQUIRE(ldl % 8 == 0 && ldl <= CE_MAX_VEC * 256, "ce: padded vocab must be a multiple of 8 and <= %d", CE_MAX_VEC * 256);
-  const int blocks = sk_ce_blocks(M);
+  SK_REQUIRE(ldl % 8 == 0 && V <= ldl, "ce: padded vocab must be a multiple of 8 and >= the vocabulary");
   const float gs = num_items > 0.f ? dloss / num_items : dloss;
-  ce_fwd_bwd_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(logits, labels, dlogits, partial, row_nll, row_weight, M, T, V, ldl, gs);
+  int blocks;
+  if (ldl <= CE_MAX_VEC * 256) {             // unit vocabularies (502): one warp per row, the row lives in registers
+    blocks = (M + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    ce_fwd_bwd_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(logits, labels, dlogits, partial, row_nll, row_weight, M, T, V, ldl, gs);
+  } else {                                   // text + unit vocabularies: one block per row, two passes
+    blocks = M;
+    ce_large_kernel<<<blocks, 256, 0, s>>>(logits, labels, dlogits, partial, row_nll, row_weight, M, T, V, ldl, gs);
+  }
   SK_LAUNCH_CHECK();
   ce_finalize_kernel<<<1, 256, 0, s>>>(partial, blocks, num_items, stats_out);
   SK_LAUNCH_CHECK();

@@ -300,7 +300,8 @@ int sk_lm_create(const SkLmConfig* cfg, SkLm** out) {
   SK_REQUIRE(cfg->hidden % 8 == 0 && cfg->hidden <= 1024, "sk_lm_create: hidden must be a multiple of 8 and <= 1024");
   SK_REQUIRE(cfg->ffn % 8 == 0, "sk_lm_create: ffn must be a multiple of 8");
   SK_REQUIRE(cfg->n_heads % cfg->n_kv_heads == 0, "sk_lm_create: n_heads must be a multiple of n_kv_heads");
-  SK_REQUIRE(cfg->vocab_size > 0 && cfg->vocab_size <= 512, "sk_lm_create: vocab_size must be in [1,512] (unit vocab)");
+  SK_REQUIRE(cfg->vocab_size > 0 && cfg->vocab_size <= (1 << 20),
+             "sk_lm_create: vocab_size must be in [1, 2^20] (unit vocabularies are ~502, interleaved text+unit ones ~152 k)");
   SkLm* lm = new SkLm();
   lm->cfg = *cfg;
   lm->d = cfg->hidden;

@@ -238,6 +238,32 @@ def test_cross_entropy_fwd_bwd(num_items):
     assert float(d[:, -1].float().abs().max()) == 0.0  # last position has no target
 
 
+@pytest.mark.parametrize("V,Vp,rows", [(5003, 5056, 40), (152167, 152192, 12)])
+def test_ce_large_vocabulary(V, Vp, rows):
+    """Text + unit vocabularies (interleaved tokeniser, ~152 k columns): the block-per-row two-pass kernel."""
+    from slamkit_b200 import ops
+    from oracle.lm_oracle import compute_loss
+    B, T = 2, rows
+    logits = torch.zeros(B, T, Vp, dtype=torch.bfloat16)
+    logits[..., :V] = _randn(B, T, V, seed=4, scale=3.0)
+    logits[..., V:] = 9.0
+    g = torch.Generator().manual_seed(5)
+    labels = torch.randint(0, V, (B, T), generator=g)
+    labels[0, 3] = V - 1            # last real column
+    labels[1, rows // 2:] = -100
+    num_items = float((labels[:, 1:] != -100).sum())
+    lf = logits[..., :V].float().requires_grad_(True)
+    ref_loss = compute_loss(lf, labels, num_items)
+    ref_loss.backward()
+    stats, dlogits, row_nll = ops.ce_fwd_bwd(logits.view(B * T, Vp).to(DEV), labels.view(-1).to(DEV), T, V, num_items)
+    assert abs(float(stats[0]) - float(ref_loss)) < 1e-5 * abs(float(ref_loss))
+    assert int(stats[1]) == int(num_items)
+    d = dlogits.cpu().view(B, T, Vp)
+    assert rel_err(d[..., :V], lf.grad) < 4e-3, rel_err(d[..., :V], lf.grad)
+    assert float(d[..., V:].float().abs().max()) == 0.0
+    assert float(d[:, -1].float().abs().max()) == 0.0
+
+
 # ---------------------------------------------------------------------------------------------- attention
 def _attn_ref(qkv, B, T, H, KVH, causal, scale, d_o=None):
     hd = 64

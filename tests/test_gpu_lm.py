@@ -206,6 +206,27 @@ def test_lm_packed_batch_equals_separate_documents():
     assert torch.isfinite(grads_packed.float()).all()
 
 
+def test_lm_large_vocabulary_vs_oracle():
+    """A vocabulary far above the unit-only 502 (the interleaved text+unit configuration): lm_head GEMMs with thousands
+    of columns, the block-per-row CE kernel, a larger tied embedding in the optimiser."""
+    from oracle import lm_oracle as O
+    cfg_o = O.OracleLMConfig(vocab_size=4099, hidden=128, n_layers=2, n_heads=2, n_kv_heads=1, head_dim=64, ffn=256)
+    m, p = _mk(cfg_o, 7, 2, 96)
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(1, 4099, (2, 96), generator=g)
+    labels = ids.clone()
+    labels[1, 70:] = -100
+    n_items = float((labels[:, 1:] != -100).sum())
+    out = m.forward_backward(ids, labels, num_items_in_batch=n_items)
+    lo, lg_o, go = O.forward_backward(p, cfg_o, ids, labels, n_items)
+    assert abs(float(out.loss) - float(lo)) < 1e-3 * abs(float(lo)), (float(out.loss), float(lo))
+    lg = m.forward(ids).logits.float().cpu()
+    assert lg.shape[-1] == 4099 and rel_err(lg, lg_o.float()) < 8e-3
+    got = m.state_dict_hf(grads=True)
+    for k in ("lm.model.embed_tokens.weight", "lm.model.layers.1.mlp.down_proj.weight", "lm.model.norm.weight"):
+        assert rel_err(got[k].float().cpu(), go[k].float()) < 3e-2, (k, rel_err(got[k].float().cpu(), go[k].float()))
+
+
 def test_grad_norm_and_clip_matches_torch():
     from oracle import lm_oracle as O
     from slamkit_b200.lm import B200AdamW
