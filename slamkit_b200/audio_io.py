@@ -1,8 +1,10 @@
-"""Minimal audio file I/O for cli/extract_features.py: PCM WAV via the standard library (no torchaudio / soundfile in
-the image).  Mirrors what `WavDataset.__getitem__` does after decoding (cli/extract_features.py:50-57): resample to the
-target rate if needed, mix down to mono, return float32 in [-1, 1).  FLAC decoding is a SURVEY.md §8(f-3) item."""
+"""Audio file I/O for cli/extract_features.py: PCM WAV via the standard library, FLAC via the library's own decoder
+(`sk_flac_*`; the image has no audio backend).  Mirrors what `WavDataset.__getitem__` does after decoding
+(cli/extract_features.py:50-57): resample to the target rate if the file's differs (`torchaudio.functional.resample`
+defaults: Hann-windowed sinc, lowpass_filter_width 6, rolloff 0.99), THEN average the channels, float32 in [-1, 1)."""
 from __future__ import annotations
 
+import math
 import wave
 from typing import Tuple
 
@@ -13,6 +15,39 @@ import torch
 def wav_num_frames(path: str) -> int:
     with wave.open(path, "rb") as w:
         return w.getnframes()
+
+
+def resample(x: torch.Tensor, orig_sr: int, new_sr: int, lowpass_filter_width: int = 6, rolloff: float = 0.99) -> torch.Tensor:
+    """Band-limited resampling with the arithmetic of `torchaudio.functional.resample(x, orig_sr, new_sr)` at its default
+    arguments (the call at cli/extract_features.py:53-54): reduce the rates by their gcd, build `new` polyphase
+    Hann-windowed sinc filters of cutoff `rolloff * min(orig, new)` in float32, run them as a
+    stride-`orig` convolution over the zero-padded waveform and keep ceil(new * n / orig) samples.
+    x: [..., frames] float32.  Pinned against torchaudio in tests/test_host_cpu.py."""
+    if orig_sr == new_sr:
+        return x
+    g = math.gcd(int(orig_sr), int(new_sr))
+    orig, new = int(orig_sr) // g, int(new_sr) // g
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    # torchaudio builds the taps in the waveform's dtype (float32 here), not in float64: for ratios such as 441 -> 160
+    # that moves individual taps by ~1e-5, so the restatement keeps float32 throughout
+    f32 = torch.float32
+    idx = torch.arange(-width, width + orig, dtype=f32)[None, None] / orig
+    t = torch.arange(0, -new, -1, dtype=f32)[:, None, None] / new + idx
+    t *= base
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    kern = torch.where(t == 0, torch.tensor(1.0, dtype=f32), t.sin() / t)
+    kern *= window * (base / orig)                                  # [new, 1, 2*width + orig]
+    shape = x.shape
+    w = x.reshape(-1, shape[-1]).to(torch.float32)
+    n = w.shape[-1]
+    w = torch.nn.functional.pad(w, (width, width + orig))
+    y = torch.nn.functional.conv1d(w[:, None], kern, stride=orig)   # [rows, new, frames/orig]
+    y = y.transpose(1, 2).reshape(w.shape[0], -1)
+    target = math.ceil(new * n / orig)
+    return y[..., :target].reshape(shape[:-1] + (target,))
 
 
 def load_wav(path: str, target_sr: int = 16000) -> torch.Tensor:
@@ -28,11 +63,8 @@ def load_wav(path: str, target_sr: int = 16000) -> torch.Tensor:
     else:
         raise ValueError(f"{path}: unsupported PCM sample width {width}")
     x = torch.from_numpy(x.reshape(-1, ch).T.copy())          # [channels, frames]
-    if sr != target_sr:
-        # band-limited resampling by linear interpolation of a sinc-free grid is NOT what torchaudio does; refuse rather
-        # than silently produce different unit ids
-        raise ValueError(f"{path}: sample rate {sr} != {target_sr}; resample offline (SURVEY.md §8 f-3)")
-    return x.mean(dim=0) if x.shape[0] > 1 else x[0]
+    x = resample(x, sr, target_sr)                            # reference order: resample, then the channel mean
+    return x.mean(dim=0)
 
 
 def write_wav(path: str, x: torch.Tensor, sr: int = 16000) -> None:
@@ -72,11 +104,9 @@ def flac_decode_int(path: str) -> np.ndarray:
 def load_flac(path: str, target_sr: int = 16000) -> torch.Tensor:
     """torchaudio.load semantics for integer FLAC: float32 = int / 2^(bits-1), then the channel mean."""
     info = flac_info(path)
-    if info["sample_rate"] != target_sr:
-        raise ValueError(f"{path}: sample rate {info['sample_rate']} != {target_sr}; resample offline")
     pcm = flac_decode_int(path).astype(np.float32) / float(1 << (info["bits_per_sample"] - 1))
-    x = torch.from_numpy(pcm.T.copy())
-    return x.mean(dim=0) if x.shape[0] > 1 else x[0]
+    x = resample(torch.from_numpy(pcm.T.copy()), info["sample_rate"], target_sr)
+    return x.mean(dim=0)
 
 
 def load_audio(path: str, target_sr: int = 16000) -> torch.Tensor:

@@ -183,6 +183,36 @@ def test_prepare_tokens_cli_reproduces_reference_golden(golden_dir, tmp_path):
         assert tok.prepare_sample(ln)["input_ids"] == z[f"ids{i}"].tolist()
 
 
+@pytest.mark.parametrize("orig,new,n", [(44100, 16000, 50001), (8000, 16000, 7777), (48000, 16000, 96000),
+                                        (22050, 16000, 30000), (24000, 16000, 16001), (32000, 16000, 5)])
+def test_resampler_is_bit_identical_to_torchaudio(orig, new, n):
+    """cli/extract_features.py:53-54 resamples with torchaudio.functional.resample's defaults; the host restatement in
+    slamkit_b200.audio_io must give the same samples (float32 taps, stride-`orig` polyphase convolution)."""
+    torchaudio = pytest.importorskip("torchaudio")
+    from slamkit_b200.audio_io import resample
+    g = torch.Generator().manual_seed(orig + new)
+    x = torch.rand(2, n, generator=g) * 2 - 1
+    assert torch.equal(resample(x, orig, new), torchaudio.functional.resample(x, orig, new))
+    assert resample(x, new, new) is x
+
+
+def test_load_wav_resamples_then_mixes_down(tmp_path):
+    """WavDataset.__getitem__ order (cli/extract_features.py:52-57): resample each channel, then the channel mean."""
+    torchaudio = pytest.importorskip("torchaudio")
+    import wave
+    from slamkit_b200.audio_io import load_audio
+    g = torch.Generator().manual_seed(0)
+    pcm = torch.randint(-20000, 20000, (4410, 2), generator=g, dtype=torch.int32).to(torch.int16)
+    path = str(tmp_path / "stereo44k.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(44100)
+        w.writeframes(pcm.numpy().tobytes())
+    got = load_audio(path, 16000)
+    x = (pcm.float() / 32768.0).t().contiguous()
+    want = torchaudio.functional.resample(x, 44100, 16000).mean(dim=0)
+    assert got.shape == (1600,) and torch.equal(got, want)
+
+
 def test_wav_io_roundtrip(tmp_path):
     from slamkit_b200.audio_io import load_wav, wav_num_frames, write_wav
     x = (0.3 * torch.randn(12345, generator=torch.Generator().manual_seed(0))).clamp(-1, 1)
