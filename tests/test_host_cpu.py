@@ -269,3 +269,41 @@ def test_flac_decoder_on_reference_example_audio():
         pcm = flac_decode_int(os.path.join(base, name))
         assert info["num_frames"] == n and pcm.shape == (n, 1)
         assert hashlib.md5(pcm.astype("<i2").tobytes()).digest() == info["md5"]
+
+
+def test_preference_alignment_cli_host_path(tmp_path):
+    """Config composition and data path of cli/preference_alignment_train.py (reference: cli/preference_alignment_train.py,
+    config/preference_alignment_train.yaml, slamkit/data/hf_dataset.py:127-148, slam_dpo_trainer.py:40-64)."""
+    from cli.preference_alignment_train import auto_bleu, load_pairs, tokenize_pairs
+    from slamkit_b200.config import load_config
+    from slamkit_b200.dpo import collate_pairs
+    from slamkit_b200.tokeniser import B200UnitTokeniser
+    cfg = load_config("preference_alignment_train", ["data.train_path=pairs.jsonl", "data.val_path=null"])
+    ta = cfg.training_args
+    assert ta.learning_rate == 5e-5 and ta.beta == 0.1 and ta.max_grad_norm == 0.5 and ta.lr_scheduler_type == "cosine_with_min_lr"
+    assert cfg.data.repetition_filter is True and cfg.data.auto_bleu_n == 2 and cfg.data.max_auto_bleu == 0.3
+    assert cfg.tokeniser.params.load_fe is False and cfg.model.tlm_type == "twist"
+    from cli.train import parse_run_time
+    assert parse_run_time(cfg.run_time) == 6 * 3600        # YAML 1.1 reads 6:00:00 as the sexagesimal integer 21600
+    # auto-BLEU: share of n-grams that occur more than once (calc_auto_bleu)
+    assert auto_bleu("the cat the cat sat", 2) == 0.5 and auto_bleu("a b c d", 2) == 0.0 and auto_bleu("one", 2) == 0.0
+    rows = [
+        {"prompt": "<Un1><Un2>", "chosen": "<Un3><Un4>", "rejected": "<Un5>", "prompt_text": "he said", "chosen_text": "hello there", "extra": 1},
+        {"prompt": "<Un7>", "chosen": "<Un8>", "rejected": "<Un9>", "prompt_text": "go go go go", "chosen_text": "go go go", "extra": 2},
+        {"prompt": "<Un10><Un11><Un12>", "chosen": "<Un13>", "rejected": "<Un14><Un15>", "prompt_text": "a b", "chosen_text": "c d", "extra": 3},
+    ]
+    path = tmp_path / "pairs.jsonl"
+    path.write_text("\n".join(json.dumps(r) for r in rows) + "\n")
+    kept = load_pairs(str(path), True, 2, 0.3)
+    assert [r["prompt"] for r in kept] == ["<Un1><Un2>", "<Un10><Un11><Un12>"] and set(kept[0]) == {"prompt", "chosen", "rejected"}
+    assert len(load_pairs(str(path), False, 2, 0.3)) == 3
+    tok = B200UnitTokeniser(None, dedup=True, bos_eos_token_id=1, pad_token_id=0, num_units=500, load_fe=False)
+    t = tokenize_pairs(kept, tok, max_prompt_length=2, max_length=3)
+    assert t[0]["prompt_input_ids"] == [3, 4] and t[1]["prompt_input_ids"] == [13, 14]    # left-truncated: the BOS drops first
+    assert t[0]["chosen_input_ids"] == [5] and t[1]["rejected_input_ids"] == [16]          # room = max_length - len(prompt) = 1
+    full = tokenize_pairs(kept, tok, max_prompt_length=None, max_length=None)
+    assert full[0]["prompt_input_ids"] == [1, 3, 4] and full[0]["chosen_input_ids"] == [5, 6, 1] and full[0]["rejected_input_ids"] == [7, 1]
+    ids, labels = collate_pairs(full[:1], 0)               # one pair -> [prompt+chosen ; prompt+rejected]
+    assert ids.shape == (2, 6) and ids[0].tolist() == [1, 3, 4, 5, 6, 1] and labels[0].tolist() == [-100, -100, -100, 5, 6, 1]
+    assert ids[1].tolist() == [1, 3, 4, 7, 1, 0] and labels[1].tolist() == [-100, -100, -100, 7, 1, -100]
+    assert collate_pairs(full, 0)[0].shape == (4, 7)
