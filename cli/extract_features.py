@@ -23,7 +23,7 @@ from slamkit_b200.config import load_config, require  # noqa: E402
 logger = logging.getLogger(__name__)
 
 
-def build_tokeniser(cfg, device: str):
+def build_tokeniser(cfg, device: str, max_batch=None):
     from slamkit_b200.feature_extractor import HubertB200Config, HubertB200FeatureExtractor, random_params
     from slamkit_b200.integration import hubert_b200_from_cfg
     from slamkit_b200.tokeniser import B200UnitTokeniser
@@ -33,14 +33,15 @@ def build_tokeniser(cfg, device: str):
     if t.feature_extractor_type not in ("hubert", "hubert_b200"):
         raise ValueError(f"Unknown feature extractor type: {t.feature_extractor_type}")   # audio_tokeniser.py:104
     fe_args = dict(t.feature_extractor)
+    max_batch = max_batch or cfg.batch_size
     fe = None
     if t.params.get("load_fe", True):
         if cfg.get("synthetic_weights", False):
             hc = HubertB200Config(layer=fe_args["layer"], n_units=fe_args["num_units"])
-            fe = HubertB200FeatureExtractor(hc, random_params(hc, seed=0), device=device, max_batch=cfg.batch_size,
+            fe = HubertB200FeatureExtractor(hc, random_params(hc, seed=0), device=device, max_batch=max_batch,
                                             max_samples=16000 * 30, load_config_only=fe_args.get("load_config_only", False))
         else:
-            fe = hubert_b200_from_cfg(**fe_args, device=device, max_batch=cfg.batch_size)
+            fe = hubert_b200_from_cfg(**fe_args, device=device, max_batch=max_batch)
     p = t.params
     return B200UnitTokeniser(fe, dedup=p.dedup, bos_eos_token_id=p.get("bos_eos_token_id", 1), pad_token_id=p.pad_token_id,
                              num_units=p.get("num_units") or fe_args["num_units"], load_fe=p.get("load_fe", True))

@@ -307,3 +307,31 @@ def test_preference_alignment_cli_host_path(tmp_path):
     assert ids.shape == (2, 6) and ids[0].tolist() == [1, 3, 4, 5, 6, 1] and labels[0].tolist() == [-100, -100, -100, 5, 6, 1]
     assert ids[1].tolist() == [1, 3, 4, 7, 1, 0] and labels[1].tolist() == [-100, -100, -100, 7, 1, -100]
     assert collate_pairs(full, 0)[0].shape == (4, 7)
+
+
+def test_preference_feature_extractor_host_path(tmp_path):
+    """cli/preference_alignment_feature_extractor.py: triplet batching order [prompts, chosens, rejecteds] and how the
+    representations are split back into the rows (reference pad_collate_fn / extract_features, :50-82)."""
+    from cli.preference_alignment_feature_extractor import attach, collate_triplets, read_triplets
+    from slamkit_b200.audio_io import write_wav
+    from slamkit_b200.config import load_config
+    cfg = load_config("preference_alignment_feature_extractor", ["data_path=a.jsonl", "out_path=b.jsonl"])
+    assert cfg.batch_size == 8 and cfg.sample_rate == 16000 and cfg.skip is None and cfg.tokeniser.tokeniser_type == "unit"
+    rows = []
+    for i in range(3):
+        r = {"id": i}
+        for j, k in enumerate(("prompt", "chosen", "rejected")):
+            pth = str(tmp_path / f"{k}{i}.wav")
+            write_wav(pth, torch.full((100 * (i + 1) + 10 * j,), 0.01 * (3 * i + j + 1)))
+            r[f"{k}_path"] = pth
+        rows.append(r)
+    (tmp_path / "t.jsonl").write_text("\n".join(json.dumps(r) for r in rows) + "\n")
+    got = read_triplets(str(tmp_path / "t.jsonl"), skip=1, take=None)
+    assert [r["id"] for r in got] == [1, 2]
+    wav, lens = collate_triplets(got)
+    assert lens.tolist() == [200, 300, 210, 310, 220, 320] and wav.shape == (6, 320)
+    assert abs(float(wav[2, 0]) - 0.05) < 1e-4 and float(wav[0, 250]) == 0.0          # chosen of row 1; zero padding
+    reps = [{"units": [k], "duration": [1]} for k in range(6)]
+    out = attach(got, reps)
+    assert out[0]["prompt"]["units"] == [0] and out[1]["prompt"]["units"] == [1] and out[0]["chosen"]["units"] == [2]
+    assert out[1]["rejected"]["units"] == [5] and json.loads(json.dumps(out[0]))["id"] == 1
