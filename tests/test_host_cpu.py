@@ -335,3 +335,31 @@ def test_preference_feature_extractor_host_path(tmp_path):
     out = attach(got, reps)
     assert out[0]["prompt"]["units"] == [0] and out[1]["prompt"]["units"] == [1] and out[0]["chosen"]["units"] == [2]
     assert out[1]["rejected"]["units"] == [5] and json.loads(json.dumps(out[0]))["id"] == 1
+
+
+def test_ctypes_call_sites_match_header_arity():
+    """The Python side calls the C ABI through untyped ctypes: a changed prototype would only show up as garbage on the
+    GPU.  Every `lib.sk_*(...)` call in the package, bench, tools and tests must pass exactly as many arguments as
+    include/slamkit_b200.h declares."""
+    import ast
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "slamkit_b200.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(sk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    assert len(protos) >= 60
+    files = glob.glob(os.path.join(root, "slamkit_b200", "*.py")) + glob.glob(os.path.join(root, "tools", "*.py")) + \
+        glob.glob(os.path.join(root, "tests", "*.py")) + [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    bad, seen = [], set()
+    for f in files:
+        for node in ast.walk(ast.parse(open(f).read())):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in protos \
+                    and not any(isinstance(a, ast.Starred) for a in node.args):
+                seen.add(node.func.attr)
+                if len(node.args) != protos[node.func.attr]:
+                    bad.append((os.path.relpath(f, root), node.lineno, node.func.attr, len(node.args), protos[node.func.attr]))
+    assert not bad, bad
+    assert {"sk_lm_forward_backward", "sk_hubert_units", "sk_gemm_bf16_ws", "sk_attn_tc_bwd", "sk_seg_bounds"} <= seen
