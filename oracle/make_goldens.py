@@ -9,6 +9,8 @@ What is pinned:
                    + autograd backward under bf16 autocast, then `clip_grad_norm_(0.5)` + `torch.optim.AdamW`
                    (fused) for one step, on seeded weights / tokens.  Shapes: 2 layers, hidden 128, 2 q-heads x 64,
                    1 kv-head, ffn 256, vocab 502, batch [2, 48] with right padding (labels -100).
+  lm_packed.npz    the same reference model on a packed row (4 documents, restarting position_ids) with the explicit
+                   block-diagonal causal 4-D mask: pins the oracle's `packed=True` path bit-exactly.
   tokeniser.npz    reference `UnitTokeniser` (load_fe=False) ids for the two example_data strings and the dedup of
                    example_data/features.jsonl (units/durations are already golden files of the reference).
   hubert_tiny.npz  reference `HubertFeatureExtractor.extract` + `batch_cluster` (HF HubertModel, sklearn
@@ -117,6 +119,62 @@ def make_lm_golden(out_path: str):
     print("lm golden: loss", loss.item(), "total_norm", float(total_norm), "->", out_path)
 
 
+def _reference_unit_lm(ocfg, seed_params: int):
+    """The reference's own UnitLM (-> HF Qwen2ForCausalLM) on the oracle's seeded parameters."""
+    from oracle.lm_oracle import init_params
+    from slamkit.model.unit_lm import UnitLM, UnitLMConfig
+    tmp = tempfile.mkdtemp()
+    json.dump({
+        "architectures": ["Qwen2ForCausalLM"], "model_type": "qwen2", "hidden_size": ocfg.hidden,
+        "intermediate_size": ocfg.ffn, "num_hidden_layers": ocfg.n_layers, "num_attention_heads": ocfg.n_heads,
+        "num_key_value_heads": ocfg.n_kv_heads, "vocab_size": ocfg.vocab_size, "rms_norm_eps": ocfg.rms_eps,
+        "max_position_embeddings": 2048, "tie_word_embeddings": True, "hidden_act": "silu",
+        "rope_parameters": {"rope_theta": ocfg.rope_theta, "rope_type": "default"},
+        "use_sliding_window": False, "attention_dropout": 0.0, "torch_dtype": "bfloat16",
+    }, open(os.path.join(tmp, "config.json"), "w"))
+    cfg = UnitLMConfig(base_model_name=tmp, vocab_size=ocfg.vocab_size, twist_init=False, torch_dtype="bfloat16")
+    torch.manual_seed(0)
+    model = UnitLM(cfg)
+    params = init_params(ocfg, seed=seed_params)
+    model.load_state_dict({**params, "lm.lm_head.weight": params["lm.model.embed_tokens.weight"]}, strict=True)
+    return model, params
+
+
+def make_lm_packed_golden(out_path: str):
+    """Packed batch (DataCollatorWithFlattening layout: one row, position_ids restarting per document).  The reference
+    runs such batches through flash-attention's varlen path, which needs a GPU; the same attention pattern is given to
+    the reference model here as an explicit 4-D block-diagonal causal mask (HF passes 4-D masks through unchanged), so
+    the fixture is still produced by the reference's own UnitLM / HF Qwen2 code."""
+    from oracle.lm_oracle import OracleLMConfig, packed_mask
+    ocfg = OracleLMConfig(vocab_size=502, hidden=128, n_layers=2, n_heads=2, n_kv_heads=1, head_dim=64, ffn=256)
+    model, _ = _reference_unit_lm(ocfg, 123)
+    model.eval()
+    g = torch.Generator().manual_seed(9)
+    lens = [20, 1, 33, 42]
+    docs = [torch.randint(2, 502, (n,), generator=g) for n in lens]
+    ids = torch.cat(docs)[None]
+    pos = torch.cat([torch.arange(n) for n in lens])[None]
+    labels = ids.clone()
+    for a in np.cumsum([0] + lens[:-1]):
+        labels[0, a] = -100                        # DataCollatorWithFlattening: separator on each document's first token
+    num_items = float((labels[:, 1:] != -100).sum())
+    T = ids.shape[1]
+    mask4d = torch.zeros(1, 1, T, T, dtype=torch.bfloat16).masked_fill(~packed_mask(pos), torch.finfo(torch.bfloat16).min)
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=mask4d, position_ids=pos, labels=labels, num_items_in_batch=num_items)
+        alone = [model(input_ids=d[None]).logits[0] for d in docs]
+    off = 0
+    for n, a in zip(lens, alone):                  # each document alone == its slice of the packed row (bf16 noise)
+        assert float((a.float() - out.logits[0, off:off + n].float()).abs().max()) < 2e-2
+        off += n
+    np.savez_compressed(out_path, ids=ids.numpy(), position_ids=pos.numpy(), labels=labels.numpy(),
+                        num_items=np.float32(num_items), loss=np.float32(out.loss.item()),
+                        logits_u16=bf16_to_u16(out.logits), lens=np.array(lens, dtype=np.int64),
+                        cfg=np.array([ocfg.vocab_size, ocfg.hidden, ocfg.n_layers, ocfg.n_heads, ocfg.n_kv_heads,
+                                      ocfg.head_dim, ocfg.ffn], dtype=np.int64))
+    print("lm packed golden: loss", out.loss.item(), "->", out_path)
+
+
 def make_tokeniser_golden(out_path: str):
     from slamkit.tokeniser.unit_tokeniser import UnitTokeniser
 
@@ -188,9 +246,11 @@ if __name__ == "__main__":
     sys.path.insert(0, REF)
     gd = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gd, exist_ok=True)
-    which = sys.argv[1:] or ["lm", "tokeniser", "hubert"]
+    which = sys.argv[1:] or ["lm", "packed", "tokeniser", "hubert"]
     if "lm" in which:
         make_lm_golden(os.path.join(gd, "lm_tiny.npz"))
+    if "packed" in which:
+        make_lm_packed_golden(os.path.join(gd, "lm_packed.npz"))
     if "tokeniser" in which:
         make_tokeniser_golden(os.path.join(gd, "tokeniser.npz"))
     if "hubert" in which:

@@ -206,6 +206,21 @@ def test_lm_packed_batch_equals_separate_documents():
     assert torch.isfinite(grads_packed.float()).all()
 
 
+def test_lm_packed_matches_reference_golden(golden_dir):
+    """tests/golden/lm_packed.npz (reference UnitLM with the explicit block-diagonal mask): loss and logits of the packed
+    row through sk_lm_forward with position_ids."""
+    from oracle import lm_oracle as O
+    z = np.load(os.path.join(golden_dir, "lm_packed.npz"))
+    c = z["cfg"]
+    cfg_o = O.OracleLMConfig(vocab_size=int(c[0]), hidden=int(c[1]), n_layers=int(c[2]), n_heads=int(c[3]),
+                             n_kv_heads=int(c[4]), head_dim=int(c[5]), ffn=int(c[6]))
+    m, _ = _mk(cfg_o, 123, 1, 128)
+    ids, pos, labels = (torch.from_numpy(z[k]) for k in ("ids", "position_ids", "labels"))
+    out = m.forward(ids, position_ids=pos, labels=labels, num_items_in_batch=float(z["num_items"]))
+    assert abs(float(out.loss) - float(z["loss"])) < 1e-3 * abs(float(z["loss"])), (float(out.loss), float(z["loss"]))
+    assert rel_err(out.logits[0].float().cpu(), u16_to_bf16(z["logits_u16"])[0].float()) < 8e-3
+
+
 def test_lm_large_vocabulary_vs_oracle():
     """A vocabulary far above the unit-only 502 (the interleaved text+unit configuration): lm_head GEMMs with thousands
     of columns, the block-per-row CE kernel, a larger tied embedding in the optimiser."""

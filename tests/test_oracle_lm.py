@@ -106,3 +106,19 @@ def test_packed_mask_equals_running_documents_separately():
         off += n
     leaky = O.forward_logits(p, cfg, ids, pos, packed=False)[0]       # same row without the document mask
     assert float((leaky[lens[0]:] - packed[lens[0]:]).abs().max()) > 1e-3
+
+
+def test_packed_batch_matches_reference_golden(golden_dir):
+    """tests/golden/lm_packed.npz: the reference's UnitLM (HF Qwen2) on a packed row with the explicit block-diagonal
+    causal 4-D mask -- the oracle's `packed=True` path reproduces its logits bit for bit and its loss to 1e-6."""
+    z = np.load(os.path.join(golden_dir, "lm_packed.npz"))
+    c = z["cfg"]
+    cfg = O.OracleLMConfig(vocab_size=int(c[0]), hidden=int(c[1]), n_layers=int(c[2]), n_heads=int(c[3]),
+                           n_kv_heads=int(c[4]), head_dim=int(c[5]), ffn=int(c[6]))
+    p = O.init_params(cfg, seed=123)
+    ids, pos, labels = (torch.from_numpy(z[k]) for k in ("ids", "position_ids", "labels"))
+    logits = O.forward_logits(p, cfg, ids, pos, packed=True)
+    assert torch.equal(logits, u16_to_bf16(z["logits_u16"]))
+    loss = O.compute_loss(logits, labels, float(z["num_items"]))
+    assert abs(float(loss) - float(z["loss"])) < 1e-6 * abs(float(z["loss"]))
+    assert O.document_ids(pos.clone())[0, -1] == len(z["lens"])
