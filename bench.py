@@ -405,8 +405,12 @@ def main():
     hubert = None
     if not args.skip_hubert:
         del devb
-        hubert = run_hubert_gpu(args, rank, local_rank, world, lib, dist)
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            hubert = run_hubert_gpu(args, rank, local_rank, world, lib, dist)
+        except Exception as e:      # the secondary leg must never cost the primary line
+            hubert = {"metric": "HuBERT-25Hz unit extraction audio-hours/sec", "value": None,
+                      "error": f"{type(e).__name__}: {e}"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline and hubert.get("value") is not None:
             import subprocess
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--hubert-cpu"], capture_output=True,
