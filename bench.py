@@ -181,22 +181,63 @@ def run_hubert_gpu(args, rank, local_rank, world, lib, dist):
     sync()
     dev_ms = mx(e0.elapsed_time(e1))
     launches = lib.sk_launch_count() - l0
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e2.record()
-    for i in range(n):
-        ids, nf = fe.units_device(host[i % 2], None)       # pinned host -> device inside
-        ids_h = ids.cpu()                                   # device -> host read of the labels (192 KB)
-    e3.record()
-    sync()
-    e2e_ms = mx(max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3))
+    def e2e_plain():
+        for i in range(n):
+            ids, nf = fe.units_device(host[i % 2], None)       # pinned host -> device inside, on the compute stream
+            ids_h = ids.cpu()                                   # device -> host read of the labels (192 KB)
+        return ids_h
+
+    def e2e_prefetch():
+        # what a loader with pinned memory does: batch i+1's audio crosses PCIe on a copy stream while batch i is
+        # extracted; every batch is still copied from pinned host memory inside the timed region
+        copy = torch.cuda.Stream(device=dev)
+        cur_stream = torch.cuda.current_stream()
+
+        def fetch(i):
+            with torch.cuda.stream(copy):
+                t = host[i % 2].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return t, ev
+
+        nxt = fetch(0)
+        for i in range(n):
+            wav_d, ev = nxt
+            cur_stream.wait_event(ev)
+            if i + 1 < n:
+                nxt = fetch(i + 1)
+            ids, nf = fe.units_device(wav_d, None)
+            wav_d.record_stream(cur_stream)
+            ids_h = ids.cpu()
+        return ids_h
+
+    def timed(fn):
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e2.record()
+        out = fn()
+        e3.record()
+        sync()
+        return out, mx(max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3))
+
+    ids_h, e2e_ms = timed(e2e_plain)
+    e2e_mode = "H2D on the compute stream"
+    if world == 1:      # (single process only: a rank-local failure must not leave the other ranks in a barrier)
+        try:
+            # accepted only if it reproduces the labels of the plain loop bit for bit (same batches, deterministic kernels)
+            ids_p, ms_p = timed(e2e_prefetch)
+            if torch.equal(ids_p, ids_h) and ms_p < e2e_ms:
+                e2e_ms, e2e_mode = ms_p, "next batch's H2D prefetched on a copy stream"
+        except Exception:
+            torch.cuda.synchronize()
     hours = HUBERT_B * 30.0 / 3600.0 * world
     out = {"metric": "HuBERT-25Hz unit extraction audio-hours/sec", "value": hours * n / (dev_ms / 1e3),
            "unit": "audio-hours/s", "batches": n, "ms_per_batch": dev_ms / n,
            "config": {"workload": "mHuBERT-25Hz geometry, 11 encoder layers + km500 argmin, batch 64 x 30 s @ 16 kHz "
                                   "synthetic audio, split-bf16 (fp32-grade) tensor-core products", "parallelism": f"dp{world}"},
            "e2e": {"value": hours * n / (e2e_ms / 1e3), "unit": "audio-hours/s",
-                   "h2d_bytes_per_step": HUBERT_B * HUBERT_S * 4, "d2h_bytes_per_step": int(ids_h.numel() * 4)},
+                   "h2d_bytes_per_step": HUBERT_B * HUBERT_S * 4, "d2h_bytes_per_step": int(ids_h.numel() * 4),
+                   "mode": e2e_mode},
            "gpu_launches": int(launches), "dtype": "bf16x3 (split) / fp32 accumulate"}
     if rank == 0:
         pk = peaks()
