@@ -158,7 +158,11 @@ int64_t sk_lm_workspace_bytes(const SkLm* lm, int B, int T);
  * workspace >= sk_lm_workspace_bytes(B,T) for the largest (B,T) used. */
 int sk_lm_bind(SkLm* lm, void* params, void* grads, const void* rope_cos, const void* rope_sin, void* workspace,
                int64_t workspace_bytes);
-/* Forward only (eval / log-likelihood): logits stay in the workspace, see sk_lm_logits. labels may be NULL. */
+/* Forward only (eval / log-likelihood): logits stay in the workspace, see sk_lm_logits. labels may be NULL.
+ * pos_ids: int32 [B*T] or NULL (positions 0..T-1 per row).  When given they drive RoPE AND mark packed documents: a
+ * document starts wherever pos_ids == 0, and tokens attend only within their document (the reference's varlen
+ * flash-attention path for DataCollatorWithFlattening batches, slamkit/data/hf_dataset.py:61-62; cli/train.py:43-45).
+ * The same holds for every sk_lm_* entry point below that takes pos_ids. */
 int sk_lm_forward(SkLm* lm, const int64_t* ids, const int64_t* labels, const int32_t* pos_ids, int B, int T,
                   float num_items, float* stats, void* stream);
 /* Forward + backward of one micro-batch. accumulate=0 overwrites grads, 1 adds (gradient accumulation).
