@@ -56,6 +56,19 @@ int sk_gemm_bf16_ws(int M, int N, int K, const void* A, int lda, int a_mn, const
                     int force_bn, void* ws, int64_t ws_bytes, void* stream);
 int64_t sk_gemm_ws_bytes(void);
 
+/* Linears of the LM step with the following element-wise op fused into the GEMM epilogue (no extra pass over HBM).
+ * sk_linear_swiglu_fwd: gu[M,2F] = x[M,K] * w_gu[2F,K]^T and act[M,F] = bf16(bf16(silu(gate)) * up)  (Qwen2MLP,
+ *   HF:models/qwen2/modeling_qwen2.py:35-48).  w_gu -- and therefore gu -- is stored in 128-row blocks: rows
+ *   [256b, 256b+128) = gate_proj rows [128b, 128b+128), rows [256b+128, 256b+256) = the same rows of up_proj; F % 128 == 0.
+ * sk_linear_swiglu_bwd: d_gu[M,2F] (same block layout) from d_act = dy[M,N] * w_down[N,F] and the saved gu; d_act is
+ *   never written.
+ * sk_linear_rope: out[M,N] = x[M,K] * w[N,K]^T + bias[N], then every 64-column head with column < rope_cols is rotated
+ *   (HF apply_rotary_pos_emb, :102-146); pos_ids int32 [M] or NULL (position = row % T), clamped to [0, max_positions). */
+int sk_linear_swiglu_fwd(int M, int F, int K, const void* x, const void* w_gu, void* gu, void* act, void* stream);
+int sk_linear_swiglu_bwd(int M, int N, int F, const void* dy, const void* w_down, const void* gu, void* dgu, void* stream);
+int sk_linear_rope(int M, int N, int K, const void* x, const void* w, const void* bias, void* out, const void* cos_t,
+                   const void* sin_t, const int32_t* pos_ids, int T, int rope_cols, int max_positions, void* stream);
+
 /* ---- causal-LM element-wise / reduction kernels (path (ii)) --------------------------------------------------- */
 /* Embedding lookup, HF:models/qwen2/modeling_qwen2.py:332-415 (embed_tokens). ids int64 [M]. */
 int sk_embed_fwd(const int64_t* ids, const void* table, void* out, int M, int D, int V, void* stream);
@@ -73,9 +86,10 @@ int sk_colsum_splits(void);
 int sk_colsum(const void* x, void* out, float* partial, int M, int N, int ld, int accumulate, void* stream);
 /* Rotary embedding (rotate_half form) in place on the first n_rot_heads heads of each row,
  * HF:models/qwen2/modeling_qwen2.py:102-146 (apply_rotary_pos_emb). cos/sin: bf16 [maxpos, head_dim/2].
- * pos_ids: int32 [M] or NULL (position = row % T). inverse=1 applies the transposed rotation (backward). */
+ * pos_ids: int32 [M] or NULL (position = row % T), clamped to [0, max_positions) = the rows of the tables.
+ * inverse=1 applies the transposed rotation (backward). */
 int sk_rope(void* qkv, const void* cos_t, const void* sin_t, const int32_t* pos_ids, int M, int T, int ld,
-            int n_rot_heads, int head_dim, int inverse, void* stream);
+            int n_rot_heads, int head_dim, int inverse, int max_positions, void* stream);
 /* Qwen2MLP activation down(silu(gate)*up), HF:models/qwen2/modeling_qwen2.py:35-48. gu = [gate | up], each F wide. */
 int sk_swiglu_fwd(const void* gu, void* act, int M, int F, void* stream);
 int sk_swiglu_bwd(const void* gu, const void* dact, void* dgu, int M, int F, void* stream);

@@ -106,6 +106,19 @@ int sk_gemm_bf16(int M, int N, int K, const void* A, int lda, int a_mn, const vo
   return sk_gemm_launch(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, out_f32, bias, residual, ldr, round_before_res, act,
                         force_bn, S(stream));
 }
+int sk_linear_swiglu_fwd(int M, int F, int K, const void* x, const void* w_gu, void* gu, void* act, void* stream) {
+  SK_REQUIRE(x && w_gu && gu && act, "sk_linear_swiglu_fwd: null operand");
+  return sk_linear_swiglu_fwd_launch(M, F, K, x, w_gu, gu, act, S(stream));
+}
+int sk_linear_swiglu_bwd(int M, int N, int F, const void* dy, const void* w_down, const void* gu, void* dgu, void* stream) {
+  SK_REQUIRE(dy && w_down && gu && dgu, "sk_linear_swiglu_bwd: null operand");
+  return sk_linear_swiglu_bwd_launch(M, N, F, dy, w_down, gu, dgu, S(stream));
+}
+int sk_linear_rope(int M, int N, int K, const void* x, const void* w, const void* bias, void* out, const void* cos_t,
+                   const void* sin_t, const int32_t* pos_ids, int T, int rope_cols, int max_positions, void* stream) {
+  SK_REQUIRE(x && w && out && cos_t && sin_t, "sk_linear_rope: null operand");
+  return sk_linear_rope_launch(M, N, K, x, w, bias, out, cos_t, sin_t, pos_ids, T, rope_cols, max_positions, S(stream));
+}
 int sk_gemm_bf16_splitk(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                         int ldc, int accumulate, void* splitk_ws, int64_t splitk_ws_bytes, void* stream) {
   SK_REQUIRE(A && B && C, "sk_gemm_bf16_splitk: null operand");
@@ -140,8 +153,9 @@ int sk_colsum(const void* x, void* out, float* partial, int M, int N, int ld, in
   return sk_colsum_launch(CBF(x), BF(out), partial, M, N, ld, accumulate, S(stream));
 }
 int sk_rope(void* qkv, const void* cos_t, const void* sin_t, const int32_t* pos_ids, int M, int T, int ld,
-            int n_rot_heads, int head_dim, int inverse, void* stream) {
-  return sk_rope_launch(BF(qkv), CBF(cos_t), CBF(sin_t), pos_ids, M, T, ld, n_rot_heads, head_dim, inverse, S(stream));
+            int n_rot_heads, int head_dim, int inverse, int max_positions, void* stream) {
+  return sk_rope_launch(BF(qkv), CBF(cos_t), CBF(sin_t), pos_ids, M, T, ld, n_rot_heads, head_dim, inverse, max_positions,
+                        S(stream));
 }
 int sk_swiglu_fwd(const void* gu, void* act, int M, int F, void* stream) {
   return sk_swiglu_fwd_launch(CBF(gu), BF(act), M, F, S(stream));

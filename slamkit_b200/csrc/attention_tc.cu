@@ -804,12 +804,6 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   const int g = h / (H / KVH);
   const int k0 = kt * AT_BC;
   const int row_base = b * T;
-  int n_qt = (T + BK_BR - 1) / BK_BR;
-  // packed batches: queries of later documents never see these keys -- stop at the end of the document of the tile's
-  // last key (seg_end[token] = in-row index one past its document)
-  if (seg_end) n_qt = min(n_qt, (seg_end[row_base + min(k0 + AT_BC, T) - 1] + BK_BR - 1) / BK_BR);
-  const int qt_begin = CAUSAL ? (k0 / BK_BR) : 0;
-  const int n_it = max(0, n_qt - qt_begin);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV128);
@@ -837,6 +831,13 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   const uint32_t tmem_base = *tmem_slot_ptr;
   griddep_wait();   // prologue (barriers, TMEM) may overlap the previous kernel's tail; its outputs are visible from here
   const uint32_t tST = tmem_base, tdPT = tmem_base + 64, tdK = tmem_base + 128, tdV = tmem_base + 192;
+  int n_qt = (T + BK_BR - 1) / BK_BR;
+  // packed batches: queries of later documents never see these keys -- stop at the end of the document of the tile's
+  // last key (seg_end[token] = in-row index one past its document).  Read AFTER griddep_wait: seg_end may have been
+  // written by the kernel this launch overlaps with (the PDL rule of common.cuh: no global access before the wait).
+  if (seg_end) n_qt = min(n_qt, (seg_end[row_base + min(k0 + AT_BC, T) - 1] + BK_BR - 1) / BK_BR);
+  const int qt_begin = CAUSAL ? (k0 / BK_BR) : 0;
+  const int n_it = max(0, n_qt - qt_begin);
 
   if (warp == 0) {
     if (lane == 0) {

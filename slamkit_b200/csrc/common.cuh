@@ -160,6 +160,14 @@ SK_DEVINL float ex2_approx(float x) {
   return y;
 }
 
+// sigmoid / SiLU via ex2.approx + rcp.approx (relative error ~2e-7, far inside the bf16 rounding every use ends in)
+SK_DEVINL float sigmoid_f(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(x * -1.4426950408889634f)));
+  return r;
+}
+SK_DEVINL float silu_f(float x) { return x * sigmoid_f(x); }
+
 // ----------------------------------------------------------------------------------------------
 // Packed fp32 pairs (sm_100a FFMA2 / FMUL2 / FADD2): two fp32 lanes per instruction issue slot.  Same fp32 FLOP rate as
 // the scalar forms (profiles/r01_micro_ffma_vs_ffma2.txt); what they buy is issue bandwidth in element-wise code.

@@ -58,6 +58,18 @@ struct GemmParams {
   int units, n_groups;  // total units, CTA groups in the grid
   float* sk_ws;         // stream-K partial tiles, one 128 x 256 fp32 slot per CTA
   uint32_t* sk_flags;   // [grid][4] publish flags (per epilogue warp), zero between launches
+  // Fused epilogues of the LM step (TMA-store path only; see SkGemmEx::epi):
+  //   1 SwiGLU forward : N = 2F laid out in [128 gate | 128 up] column blocks; writes gu through tmC AND act[M,F] =
+  //                      bf16(bf16(silu(gate)) * up) through tmAux -- the unfused swiglu_fwd_kernel's rounding points
+  //   2 SwiGLU backward: the accumulator is d_act[M,F]; reads gu (same block layout) and writes d_gu[M,2F] through tmC
+  //   3 RoPE           : after bias + bf16 rounding, every 64-column head below rope_cols is rotated (rotate_half form)
+  int epi;
+  const bf16* aux;      // epi 2: gu
+  int ld_aux;
+  const bf16* rope_cos; // epi 3: bf16 [rope_maxpos, 32]
+  const bf16* rope_sin;
+  const int* rope_pos;  // int32 [M] or null (position = row % rope_T)
+  int rope_T, rope_cols, rope_maxpos;
 };
 
 template <int BN>
@@ -284,7 +296,7 @@ template <int BN, bool A_MN, bool B_MN, bool SK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo,
-                    const __grid_constant__ CUtensorMap tmC, GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, GemmParams p) {
   using Cfg = GemmCfg<BN>;
   griddep_launch();                 // the next kernel on the stream may start its own prologue now
   extern __shared__ uint8_t smem_raw[];
@@ -479,7 +491,157 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           __syncwarp();
         }
-        if (p.tma_store) {
+        // one 64-column x 32-row bf16 chunk: registers -> this warp's swizzled staging buffer -> TMA store at (col, rows)
+        auto stage_store = [&](const CUtensorMap* map, const uint32_t (&pk)[32], int col) {
+          const uint32_t sbuf = staging_base + (uint32_t)(warp - 2) * 8192u + (store_cnt & 1u) * 4096u;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t dst = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                         "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(map, sbuf, col, m0 + q * 32);
+            tma_store_commit();
+          }
+          ++store_cnt;
+        };
+        if (!SK && p.tma_store && p.epi == 1) {
+          // ---- SwiGLU forward: tile columns [0,128) = gate, [128,256) = up of the same 128 hidden units ----
+          if constexpr (BN == 256) {
+#pragma unroll 1
+            for (int i = 0; i < 2; ++i) {
+              uint32_t gpk[32], upk[32];
+              {
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(taddr + i * 64, r0);
+                tmem_ld_32x32(taddr + i * 64 + 32, r1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                  gpk[t] = pack_bf16(__uint_as_float(r0[2 * t]), __uint_as_float(r0[2 * t + 1]));
+                  gpk[16 + t] = pack_bf16(__uint_as_float(r1[2 * t]), __uint_as_float(r1[2 * t + 1]));
+                }
+              }
+              stage_store(&tmC, gpk, n0 + i * 64);
+              {
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(taddr + 128 + i * 64, r0);
+                tmem_ld_32x32(taddr + 128 + i * 64 + 32, r1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                  upk[t] = pack_bf16(__uint_as_float(r0[2 * t]), __uint_as_float(r0[2 * t + 1]));
+                  upk[16 + t] = pack_bf16(__uint_as_float(r1[2 * t]), __uint_as_float(r1[2 * t + 1]));
+                }
+              }
+              stage_store(&tmC, upk, n0 + 128 + i * 64);
+#pragma unroll
+              for (int t = 0; t < 32; ++t) {
+                const float2 gf = unpack_bf16(gpk[t]), uf = unpack_bf16(upk[t]);
+                const float2 sb = unpack_bf16(pack_bf16(silu_f(gf.x), silu_f(gf.y)));   // bf16(silu(g))
+                gpk[t] = pack_bf16(sb.x * uf.x, sb.y * uf.y);
+              }
+              stage_store(&tmAux, gpk, (n0 >> 1) + i * 64);
+            }
+          }
+        } else if (!SK && p.tma_store && p.epi == 2) {
+          // ---- SwiGLU backward: acc = d_act; d_gate = bf16(bf16(d_act*u) * silu'(g)), d_up = bf16(d_act * bf16(silu(g))) ----
+#pragma unroll 1
+          for (int c2 = 0; c2 < BN / 64; ++c2) {
+            const int acol = n0 + c2 * 64;
+            if (acol >= p.N) break;
+            const int gcol = (acol >> 7) * 256 + (acol & 127);   // gate columns in gu / d_gu; the up columns sit 128 further
+            uint32_t gw[32], uw[32];
+            if (row_ok) {
+              const bf16* gp = p.aux + row * (size_t)p.ld_aux + gcol;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 a = ldg128(gp + 8 * j), b = ldg128(gp + 128 + 8 * j);
+                gw[4 * j] = a.x; gw[4 * j + 1] = a.y; gw[4 * j + 2] = a.z; gw[4 * j + 3] = a.w;
+                uw[4 * j] = b.x; uw[4 * j + 1] = b.y; uw[4 * j + 2] = b.z; uw[4 * j + 3] = b.w;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 32; ++t) gw[t] = uw[t] = 0u;
+            }
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(taddr + c2 * 64, r0);
+            tmem_ld_32x32(taddr + c2 * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const float a0 = __uint_as_float(t < 16 ? r0[2 * t] : r1[2 * (t - 16)]);
+              const float a1 = __uint_as_float(t < 16 ? r0[2 * t + 1] : r1[2 * (t - 16) + 1]);
+              const float2 df = unpack_bf16(pack_bf16(a0, a1));        // bf16(d_act), what the unfused path stored
+              const float2 gf = unpack_bf16(gw[t]), uf = unpack_bf16(uw[t]);
+              const float s0 = sigmoid_f(gf.x), s1 = sigmoid_f(gf.y);
+              const float sil0 = bf16_round(gf.x * s0), sil1 = bf16_round(gf.y * s1);
+              const float ds0 = s0 * (1.0f + gf.x * (1.0f - s0)), ds1 = s1 * (1.0f + gf.y * (1.0f - s1));
+              gw[t] = pack_bf16(bf16_round(df.x * uf.x) * ds0, bf16_round(df.y * uf.y) * ds1);
+              uw[t] = pack_bf16(df.x * sil0, df.y * sil1);
+            }
+            stage_store(&tmC, gw, gcol);
+            stage_store(&tmC, uw, gcol + 128);
+          }
+        } else if (!SK && p.tma_store && p.epi == 3) {
+          // ---- bias + RoPE: a 64-column chunk is one attention head; element i pairs with element i + 32 ----
+          uint32_t cw[16], sw[16];
+          {
+            int pos = 0;
+            if (row_ok) pos = p.rope_pos ? p.rope_pos[row] : (int)(row % (size_t)p.rope_T);
+            pos = max(0, min(pos, p.rope_maxpos - 1));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 c = ldg128(p.rope_cos + (size_t)pos * 32 + 8 * j), sn = ldg128(p.rope_sin + (size_t)pos * 32 + 8 * j);
+              cw[4 * j] = c.x; cw[4 * j + 1] = c.y; cw[4 * j + 2] = c.z; cw[4 * j + 3] = c.w;
+              sw[4 * j] = sn.x; sw[4 * j + 1] = sn.y; sw[4 * j + 2] = sn.z; sw[4 * j + 3] = sn.w;
+            }
+          }
+#pragma unroll 1
+          for (int c2 = 0; c2 < BN / 64; ++c2) {
+            const int col64 = n0 + c2 * 64;
+            if (col64 >= p.N) break;
+            uint32_t r0[32], r1[32], pk[32];
+            tmem_ld_32x32(taddr + c2 * 64, r0);
+            tmem_ld_32x32(taddr + c2 * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float v0[8], v1[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v0[i] = __uint_as_float(r0[g * 8 + i]);
+                v1[i] = __uint_as_float(r1[g * 8 + i]);
+              }
+              epi_bias_act(v0, p, col64 + g * 8);
+              epi_bias_act(v1, p, col64 + 32 + g * 8);
+              if (col64 < p.rope_cols) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 c = unpack_bf16(cw[g * 4 + e]), sn = unpack_bf16(sw[g * 4 + e]);
+                  const float2 x1 = unpack_bf16(pack_bf16(v0[2 * e], v0[2 * e + 1]));   // bf16 projection output
+                  const float2 x2 = unpack_bf16(pack_bf16(v1[2 * e], v1[2 * e + 1]));
+                  v0[2 * e] = bf16_round(x1.x * c.x) + bf16_round(-x2.x * sn.x);
+                  v0[2 * e + 1] = bf16_round(x1.y * c.y) + bf16_round(-x2.y * sn.y);
+                  v1[2 * e] = bf16_round(x2.x * c.x) + bf16_round(x1.x * sn.x);
+                  v1[2 * e + 1] = bf16_round(x2.y * c.y) + bf16_round(x1.y * sn.y);
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                pk[g * 4 + e] = pack_bf16(v0[2 * e], v0[2 * e + 1]);
+                pk[16 + g * 4 + e] = pack_bf16(v1[2 * e], v1[2 * e + 1]);
+              }
+            }
+            stage_store(&tmC, pk, col64);
+          }
+        } else if (p.tma_store) {
           // coalesced path: TMEM -> registers -> 128B-swizzled smem (this warp's private 32-row buffer) -> TMA store
 #pragma unroll 1
           for (int c2 = 0; c2 < BN / 64; ++c2) {
@@ -698,7 +860,7 @@ int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream
   }
   sk_prof_begin(0, stream);
   cudaError_t lerr = sk_launch_pdl_if(p.pdl != 0, gemm_tcgen05_kernel<BN, A_MN, B_MN, SK>, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, stream,
-                                   tm[0], tm[1], tm[2], tm[3], tm[4], p);
+                                   tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   sk_prof_end(stream);
   SK_CUDA_CHECK(lerr);
   SK_LAUNCH_CHECK();
@@ -767,8 +929,9 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
   const bool sk_ok = sk_env != 0 && g.batch == 1 && !use3d && g.passes == 1 && g.a_mode == 0 && g.splitk_ws != nullptr &&
                      g.splitk_ws_bytes >= sk_gemm_ws_min_bytes();
   const size_t ws_data_bytes = g.splitk_ws_bytes > SK_FLAG_BYTES ? g.splitk_ws_bytes - SK_FLAG_BYTES : 0;
-  const int BN = (g.a_mode == 1) ? 64 : sk_pick_bn(g.M * g.batch, g.N, g.force_bn);
-  CUtensorMap tm[5];
+  // the SwiGLU epilogues need both halves of a [128 gate | 128 up] block in one tile
+  const int BN = (g.a_mode == 1) ? 64 : sk_pick_bn(g.M * g.batch, g.N, (g.epi == 1 || g.epi == 2) ? 256 : g.force_bn);
+  CUtensorMap tm[6];
   const void* As[2] = {g.A, g.passes == 3 ? g.A_lo : g.A};
   const void* Bs[2] = {g.B, g.passes == 3 ? g.B_lo : g.B};
   for (int i = 0; i < 2; ++i) {
@@ -829,9 +992,36 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
   p.tma_store = 0;
   tm[4] = tm[0];
   if (!g.out_f32 && !g.C_lo && g.col_gin == 0 && p.splits == 1 && g.batch == 1 && !use3d && (g.ldc * 2) % 16 == 0) {
-    const int rc2 = sk_make_tmap_2d(&tm[4], g.C, 2, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc, 64, 32);
+    // epi 2 writes d_gu [M, 2N] (the accumulator tile is d_act [M, N])
+    const int rc2 = sk_make_tmap_2d(&tm[4], g.C, 2, (uint64_t)(g.epi == 2 ? 2 * g.N : g.N), (uint64_t)g.M, (uint64_t)g.ldc, 64, 32);
     if (rc2) return rc2;
     p.tma_store = 1;
+  }
+  tm[5] = tm[4];
+  p.epi = g.epi;
+  p.aux = reinterpret_cast<const bf16*>(g.aux);
+  p.ld_aux = g.ld_aux;
+  p.rope_cos = reinterpret_cast<const bf16*>(g.rope_cos);
+  p.rope_sin = reinterpret_cast<const bf16*>(g.rope_sin);
+  p.rope_pos = g.rope_pos;
+  p.rope_T = g.rope_T; p.rope_cols = g.rope_cols; p.rope_maxpos = g.rope_maxpos;
+  if (g.epi != 0) {
+    SK_REQUIRE(p.tma_store && g.passes == 1 && !g.residual && !g.act && g.splitk_ws == nullptr,
+               "gemm: fused epilogue %d needs the plain bf16 TMA-store path (no residual / activation / scratch)", g.epi);
+    if (g.epi == 1) {
+      SK_REQUIRE(BN == 256 && g.N % 256 == 0 && g.aux_out && g.ld_aux_out % 8 == 0 && !g.bias,
+                 "gemm: SwiGLU-forward epilogue needs N = 2F with F %% 128 == 0 and an act output");
+      const int rc3 = sk_make_tmap_2d(&tm[5], g.aux_out, 2, (uint64_t)g.N / 2, (uint64_t)g.M, (uint64_t)g.ld_aux_out, 64, 32);
+      if (rc3) return rc3;
+    } else if (g.epi == 2) {
+      SK_REQUIRE(BN == 256 && g.N % 128 == 0 && g.aux && g.ld_aux % 8 == 0 && !g.bias,
+                 "gemm: SwiGLU-backward epilogue needs N = F with F %% 128 == 0 and the saved gu activation");
+    } else if (g.epi == 3) {
+      SK_REQUIRE(g.rope_cos && g.rope_sin && g.rope_T > 0 && g.rope_maxpos > 0 && g.rope_cols % 64 == 0 && g.N % 64 == 0,
+                 "gemm: RoPE epilogue needs cos/sin tables and 64-column heads");
+    } else {
+      SK_REQUIRE(false, "gemm: unknown fused epilogue %d", g.epi);
+    }
   }
   // stream-K over the units (rows or columns of tiles) of the last, partial wave -- see WorkIter
   p.sk_units = 0;
@@ -905,4 +1095,45 @@ int sk_gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const 
   g.splitk_ws = splitk_ws;
   g.splitk_ws_bytes = splitk_ws_bytes;
   return sk_gemm_ex_launch(g, stream);
+}
+
+// ---- fused linears of the LM step (SkGemmEx::epi) ------------------------------------------------------------------
+// gu[M,2F] = x[M,K] * Wgu[2F,K]^T with Wgu (and gu) in [128 gate | 128 up] blocks, and act[M,F] = bf16(bf16(silu(gate)) * up)
+// written by the same epilogue (HF Qwen2MLP, HF:models/qwen2/modeling_qwen2.py:35-48)
+int sk_linear_swiglu_fwd_launch(int M, int F, int K, const void* x, const void* Wgu, void* gu, void* act, cudaStream_t s) {
+  SkGemmEx g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = 2 * F; g.K = K; g.batch = 1; g.passes = 1;
+  g.A = x; g.lda = K; g.B = Wgu; g.ldb = K;
+  g.C = gu; g.ldc = 2 * F;
+  g.epi = 1; g.aux_out = act; g.ld_aux_out = F;
+  g.pdl = 1;
+  return sk_gemm_ex_launch(g, s);
+}
+// d_gu[M,2F] from d_act = dy[M,N] * Wd[N,F] without materialising d_act: the epilogue turns each accumulator tile into
+// d_gate / d_up with the saved gu (autograd of the SwiGLU above, same bf16 rounding points as the unfused kernels)
+int sk_linear_swiglu_bwd_launch(int M, int N, int F, const void* dy, const void* Wd, const void* gu, void* dgu, cudaStream_t s) {
+  SkGemmEx g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = F; g.K = N; g.batch = 1; g.passes = 1;
+  g.A = dy; g.lda = N; g.B = Wd; g.ldb = F; g.b_mn = 1;
+  g.C = dgu; g.ldc = 2 * F;
+  g.epi = 2; g.aux = gu; g.ld_aux = 2 * F;
+  g.pdl = 1;
+  return sk_gemm_ex_launch(g, s);
+}
+// out[M,N] = x[M,K] * W[N,K]^T + bias, 64-column heads below rope_cols rotated in the epilogue (HF apply_rotary_pos_emb,
+// HF:models/qwen2/modeling_qwen2.py:102-146)
+int sk_linear_rope_launch(int M, int N, int K, const void* x, const void* W, const void* bias, void* out, const void* cos_t,
+                          const void* sin_t, const int32_t* pos_ids, int T, int rope_cols, int max_positions, cudaStream_t s) {
+  SkGemmEx g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.batch = 1; g.passes = 1;
+  g.A = x; g.lda = K; g.B = W; g.ldb = K;
+  g.C = out; g.ldc = N;
+  g.bias = bias;
+  g.epi = 3; g.rope_cos = cos_t; g.rope_sin = sin_t; g.rope_pos = pos_ids; g.rope_T = T;
+  g.rope_cols = rope_cols; g.rope_maxpos = max_positions;
+  g.pdl = 1;
+  return sk_gemm_ex_launch(g, s);
 }

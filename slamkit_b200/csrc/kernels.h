@@ -33,11 +33,29 @@ struct SkGemmEx {
   void* splitk_ws;          // optional scratch: deterministic split-K (few tiles, long K) and stream-K load balancing
   size_t splitk_ws_bytes;
   int pdl;                  // 1: launch with programmatic stream serialization (the LM step's short back-to-back GEMMs)
+  // Fused epilogues of the LM step (0 = none):
+  //   1 SwiGLU forward : B = gate/up weight in [128 gate rows | 128 up rows] blocks, N = 2F; C = gu [M,2F] (same block
+  //                      layout) and aux_out = act [M,F] = bf16(bf16(silu(gate)) * up)
+  //   2 SwiGLU backward: N = F, acc = d_act; aux = gu [M,2F]; C = d_gu [M,2F] (ldc = its pitch)
+  //   3 bias + RoPE    : 64-column heads with column < rope_cols are rotated with cos/sin[pos] (pos = rope_pos[row] or
+  //                      row % rope_T, clamped to [0, rope_maxpos))
+  int epi;
+  const void* aux;
+  int ld_aux;
+  void* aux_out;
+  int ld_aux_out;
+  const void *rope_cos, *rope_sin;
+  const int* rope_pos;
+  int rope_T, rope_cols, rope_maxpos;
 };
 int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream);
 int sk_gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                    int ldc, int out_f32, const void* bias, const void* residual, int ldr, int round_before_res, int act,
                    int force_bn, cudaStream_t stream, void* splitk_ws = nullptr, size_t splitk_ws_bytes = 0);
+int sk_linear_swiglu_fwd_launch(int M, int F, int K, const void* x, const void* Wgu, void* gu, void* act, cudaStream_t s);
+int sk_linear_swiglu_bwd_launch(int M, int N, int F, const void* dy, const void* Wd, const void* gu, void* dgu, cudaStream_t s);
+int sk_linear_rope_launch(int M, int N, int K, const void* x, const void* W, const void* bias, void* out, const void* cos_t,
+                          const void* sin_t, const int32_t* pos_ids, int T, int rope_cols, int max_positions, cudaStream_t s);
 
 // lm_kernels.cu
 int sk_embed_fwd_launch(const int64_t* ids, const bf16* E, bf16* out, int M, int D, int V, cudaStream_t s);
@@ -50,7 +68,7 @@ int sk_rmsnorm_bwd_launch(const bf16* dy, const bf16* x, const bf16* w, const fl
 extern "C" int sk_colsum_splits(void);
 int sk_colsum_launch(const bf16* x, bf16* out, float* partial, int M, int N, int ld, int accumulate, cudaStream_t s);
 int sk_rope_launch(bf16* qkv, const bf16* cos_t, const bf16* sin_t, const int* pos_ids, int M, int T, int ld,
-                   int n_rot_heads, int head_dim, int inverse, cudaStream_t s);
+                   int n_rot_heads, int head_dim, int inverse, int max_positions, cudaStream_t s);
 int sk_swiglu_fwd_launch(const bf16* gu, bf16* act, int M, int F, cudaStream_t s);
 int sk_swiglu_bwd_launch(const bf16* gu, const bf16* dact, bf16* dgu, int M, int F, cudaStream_t s);
 extern "C" int sk_ce_blocks(int M);

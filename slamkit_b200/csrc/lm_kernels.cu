@@ -283,7 +283,7 @@ __global__ void colsum_partial_kernel(const bf16* __restrict__ x, float* __restr
 // ------------------------------------------------------------------------------------------------
 __global__ void rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
                             const int* __restrict__ pos_ids, int M, int T, int ld, int n_rot_heads, int head_dim,
-                            int inverse) {
+                            int inverse, int max_pos) {
   griddep_launch();
   griddep_wait();
   const int half = head_dim / 2;          // 32
@@ -293,7 +293,8 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos
     const int v = (int)(i % vec_per_head);
     const int h = (int)((i / vec_per_head) % n_rot_heads);
     const int m = (int)(i / ((long)vec_per_head * n_rot_heads));
-    const int pos = pos_ids ? pos_ids[m] : (m % T);
+    int pos = pos_ids ? pos_ids[m] : (m % T);
+    pos = max(0, min(pos, max_pos - 1));     // caller-supplied positions never index outside the tables
     bf16* p1 = qkv + (size_t)m * ld + h * head_dim + v * 8;
     bf16* p2 = p1 + half;
     const uint4 a = *reinterpret_cast<const uint4*>(p1);
@@ -320,13 +321,7 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos
 // ------------------------------------------------------------------------------------------------
 // SwiGLU: gu = [gate | up] (each F wide).  act = bf16(bf16(silu(g)) * u)
 // ------------------------------------------------------------------------------------------------
-// sigmoid via ex2.approx + rcp.approx (relative error ~2e-7, far inside the bf16 rounding every use here ends in)
-SK_DEVINL float sigmoid_f(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(x * -1.4426950408889634f)));
-  return r;
-}
-SK_DEVINL float silu_f(float x) { return x * sigmoid_f(x); }
+// (sigmoid_f / silu_f: common.cuh)
 
 // two independent 16-byte vectors per thread and iteration (more loads in flight per thread)
 __global__ void __launch_bounds__(256)
@@ -839,10 +834,11 @@ int sk_colsum_launch(const bf16* x, bf16* out, float* partial, int M, int N, int
   return 0;
 }
 int sk_rope_launch(bf16* qkv, const bf16* cos_t, const bf16* sin_t, const int* pos_ids, int M, int T, int ld,
-                   int n_rot_heads, int head_dim, int inverse, cudaStream_t s) {
+                   int n_rot_heads, int head_dim, int inverse, int max_positions, cudaStream_t s) {
   SK_REQUIRE(head_dim % 16 == 0 && ld % 8 == 0, "rope: head_dim must be a multiple of 16");
+  SK_REQUIRE(max_positions > 0 && (pos_ids != nullptr || T <= max_positions), "rope: table rows (%d) do not cover T=%d", max_positions, T);
   SK_CUDA_CHECK(sk_launch_pdl(rope_kernel, dim3(grid_for((long)M * n_rot_heads * (head_dim / 16), 256)), dim3(256), (size_t)(0), s, qkv, cos_t, sin_t, pos_ids, M, T, ld,
-                                                                                   n_rot_heads, head_dim, inverse));
+                                                                                   n_rot_heads, head_dim, inverse, max_positions));
   SK_LAUNCH_CHECK();
   return 0;
 }

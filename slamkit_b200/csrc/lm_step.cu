@@ -28,7 +28,7 @@ struct LayerOff {
 struct WsLayout {
   int64_t X, h1, rstd1, qkv, ao, lse, xmid, h2, rstd2, gu, act;  // per-layer strides below
   int64_t sX, sh, srstd, sqkv, slse, sgu, sact;
-  int64_t hf, rstdf, logits, dlogits, dxA, dxB, dh, dao, dqkv, dact, dgu, delta;
+  int64_t hf, rstdf, logits, dlogits, dxA, dxB, dh, dao, dqkv, dgu, delta;
   int64_t dw_partial, colsum_partial, ce_partial, embed_scratch, splitk, splitk_bytes, attn_partial, seg_start, seg_end, total;
 };
 }  // namespace
@@ -50,9 +50,8 @@ struct SkLm {
   int* d_chunk_len = nullptr;
   int* d_tensor_chunk_begin = nullptr;
   float* d_chunk_partial = nullptr;
-  int n_chunks = 0;
+  int n_chunks = 0, n_norm_groups = 0;
   int last_B = 0, last_T = 0;
-  int attn_tc = 2;   // 0: warp-level mma.sync attention; 1: tcgen05 forward; 2: tcgen05 forward + backward (SK_ATTN_TC)
   // optional: events recorded on the compute stream as soon as a layer's gradients are final (index = layer; index
   // n_layers = lm_head / final-norm part), so the host can start that bucket's all-reduce while backward continues
   std::vector<cudaEvent_t> bwd_events;
@@ -110,7 +109,6 @@ WsLayout make_layout(const SkLm* lm, int B, int T) {
   w.dh = take(w.sX);
   w.dao = take(w.sX);
   w.dqkv = take(w.sqkv);
-  w.dact = take(w.sact);
   w.dgu = take(w.sgu);
   w.delta = take(w.slse);
   w.dw_partial = take((int64_t)sk_rmsnorm_bwd_blocks() * lm->d * 4);
@@ -153,6 +151,12 @@ int linear_wgrad(int M, int N, int K, const bf16* dy, const bf16* x, bf16* dW, i
                         splitk_ws, splitk_bytes);
 }
 
+int linear_qkv_rope(const SkLm* lm, int M, int T, const bf16* x, const bf16* W, const bf16* bias, bf16* qkv,
+                    const int32_t* pos_ids, cudaStream_t s) {
+  return sk_linear_rope_launch(M, lm->qkv_dim, lm->d, x, W, bias, qkv, lm->rope_cos, lm->rope_sin, pos_ids, T,
+                               (lm->H + lm->KVH) * lm->hd, lm->cfg.max_positions, s);
+}
+
 int check_bound(const SkLm* lm, int B, int T, const WsLayout& w) {
   SK_REQUIRE(lm->params && lm->ws, "sk_lm: sk_lm_bind has not been called");
   SK_REQUIRE(B > 0 && T > 0 && T <= lm->cfg.max_positions, "sk_lm: bad batch shape B=%d T=%d (max_positions=%d)", B, T,
@@ -174,7 +178,6 @@ int forward_impl(SkLm* lm, const int64_t* ids, const int64_t* labels, const int3
   // flash-attention path does (slamkit/data/hf_dataset.py:61-62 + HF prepare_fa_kwargs_from_position_ids)
   const int* seg_start = nullptr;
   if (pos_ids) {
-    SK_REQUIRE(lm->attn_tc >= 2, "sk_lm: position_ids (packed batches) need the tcgen05 attention kernels (SK_ATTN_TC=2)");
     SK_TRY(sk_seg_bounds_launch(pos_ids, wsp<int32_t>(lm, w.seg_start), wsp<int32_t>(lm, w.seg_end), B, T, s));
     seg_start = wsp<int32_t>(lm, w.seg_start);
   }
@@ -194,17 +197,11 @@ int forward_impl(SkLm* lm, const int64_t* ids, const int64_t* labels, const int3
     bf16* act = wsp<bf16>(lm, w.act + w.sact * l);
 
     SK_TRY(sk_rmsnorm_fwd_launch(x, P + o.ln1, h1, r1, M, d, lm->cfg.rms_eps, s));
-    SK_TRY(linear_fwd(M, lm->qkv_dim, d, h1, P + o.wqkv, qkv, lm->cfg.qkv_bias ? P + o.bqkv : nullptr, nullptr, s));
-    SK_TRY(sk_rope_launch(qkv, lm->rope_cos, lm->rope_sin, pos_ids, M, T, lm->qkv_dim, lm->H + lm->KVH, lm->hd, 0, s));
-    if (lm->attn_tc)
-      SK_TRY(sk_attn_tc_fwd_launch(qkv, ao, lse, B, T, lm->H, lm->KVH, lm->qkv_dim, d, 1, scale, s, seg_start));
-    else
-      SK_TRY(sk_attn_fwd_launch(qkv, qkv + lm->H * lm->hd, qkv + (lm->H + lm->KVH) * lm->hd, ao, lse, B, T, lm->H,
-                                lm->KVH, lm->qkv_dim, d, 1, scale, s));
+    SK_TRY(linear_qkv_rope(lm, M, T, h1, P + o.wqkv, lm->cfg.qkv_bias ? P + o.bqkv : nullptr, qkv, pos_ids, s));
+    SK_TRY(sk_attn_tc_fwd_launch(qkv, ao, lse, B, T, lm->H, lm->KVH, lm->qkv_dim, d, 1, scale, s, seg_start));
     SK_TRY(linear_fwd(M, d, d, ao, P + o.wo, xmid, nullptr, x, s));
     SK_TRY(sk_rmsnorm_fwd_launch(xmid, P + o.ln2, h2, r2, M, d, lm->cfg.rms_eps, s));
-    SK_TRY(linear_fwd(M, 2 * F, d, h2, P + o.wgu, gu, nullptr, nullptr, s));
-    SK_TRY(sk_swiglu_fwd_launch(gu, act, M, F, s));
+    SK_TRY(sk_linear_swiglu_fwd_launch(M, F, d, h2, P + o.wgu, gu, act, s));
     SK_TRY(linear_fwd(M, d, F, act, P + o.wd, xn, nullptr, xmid, s));
   }
   bf16* xL = wsp<bf16>(lm, w.X + w.sX * L);
@@ -232,7 +229,6 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
   bf16* dh = wsp<bf16>(lm, w.dh);
   bf16* dao = wsp<bf16>(lm, w.dao);
   bf16* dqkv = wsp<bf16>(lm, w.dqkv);
-  bf16* dact = wsp<bf16>(lm, w.dact);
   bf16* dgu = wsp<bf16>(lm, w.dgu);
   bf16* dlogits = wsp<bf16>(lm, w.dlogits);
   bf16* hf = wsp<bf16>(lm, w.hf);
@@ -259,24 +255,18 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
     bf16* act = wsp<bf16>(lm, w.act + w.sact * l);
 
     // MLP
-    SK_TRY(linear_dgrad(M, d, F, dxA, P + o.wd, dact, s));
+    SK_TRY(sk_linear_swiglu_bwd_launch(M, d, F, dxA, P + o.wd, gu, dgu, s));
     SK_TRY(linear_wgrad(M, d, F, dxA, act, G + o.wd, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
-    SK_TRY(sk_swiglu_bwd_launch(gu, dact, dgu, M, F, s));
     SK_TRY(linear_dgrad(M, 2 * F, d, dgu, P + o.wgu, dh, s));
     SK_TRY(linear_wgrad(M, 2 * F, d, dgu, h2, G + o.wgu, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
     SK_TRY(sk_rmsnorm_bwd_launch(dh, xmid, P + o.ln2, r2, dxA, dxB, G + o.ln2, dwp, M, d, accumulate, s));
     // attention
     SK_TRY(linear_dgrad(M, d, d, dxB, P + o.wo, dao, s));
     SK_TRY(linear_wgrad(M, d, d, dxB, ao, G + o.wo, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
-    if (lm->attn_tc >= 2)
-      SK_TRY(sk_attn_tc_bwd_launch(qkv, ao, dao, lse, wsp<float>(lm, w.delta), wsp<float>(lm, w.attn_partial), dqkv, B, T,
-                                   lm->H, lm->KVH, Q, d, Q, 1, scale, s, pos_ids ? wsp<int32_t>(lm, w.seg_start) : nullptr,
-                                   pos_ids ? wsp<int32_t>(lm, w.seg_end) : nullptr));
-    else
-      SK_TRY(sk_attn_bwd_launch(qkv, qkv + lm->H * lm->hd, qkv + (lm->H + lm->KVH) * lm->hd, ao, dao, lse,
-                                wsp<float>(lm, w.delta), dqkv, dqkv + lm->H * lm->hd, dqkv + (lm->H + lm->KVH) * lm->hd,
-                                B, T, lm->H, lm->KVH, Q, d, Q, 1, scale, s));
-    SK_TRY(sk_rope_launch(dqkv, lm->rope_cos, lm->rope_sin, pos_ids, M, T, Q, lm->H + lm->KVH, lm->hd, 1, s));
+    SK_TRY(sk_attn_tc_bwd_launch(qkv, ao, dao, lse, wsp<float>(lm, w.delta), wsp<float>(lm, w.attn_partial), dqkv, B, T,
+                                 lm->H, lm->KVH, Q, d, Q, 1, scale, s, pos_ids ? wsp<int32_t>(lm, w.seg_start) : nullptr,
+                                 pos_ids ? wsp<int32_t>(lm, w.seg_end) : nullptr));
+    SK_TRY(sk_rope_launch(dqkv, lm->rope_cos, lm->rope_sin, pos_ids, M, T, Q, lm->H + lm->KVH, lm->hd, 1, lm->cfg.max_positions, s));
     if (lm->cfg.qkv_bias)
       SK_TRY(sk_colsum_launch(dqkv, G + o.bqkv, wsp<float>(lm, w.colsum_partial), M, Q, Q, accumulate, s));
     SK_TRY(linear_dgrad(M, Q, d, dqkv, P + o.wqkv, dh, s));
@@ -298,7 +288,7 @@ int sk_lm_create(const SkLmConfig* cfg, SkLm** out) {
   SK_REQUIRE(cfg && out, "sk_lm_create: null argument");
   SK_REQUIRE(cfg->head_dim == 64, "sk_lm_create: only head_dim 64 is supported (got %d)", cfg->head_dim);
   SK_REQUIRE(cfg->hidden % 8 == 0 && cfg->hidden <= 1024, "sk_lm_create: hidden must be a multiple of 8 and <= 1024");
-  SK_REQUIRE(cfg->ffn % 8 == 0, "sk_lm_create: ffn must be a multiple of 8");
+  SK_REQUIRE(cfg->ffn % 128 == 0, "sk_lm_create: ffn must be a multiple of 128 (gate/up rows are stored in 128-row blocks)");
   SK_REQUIRE(cfg->n_heads % cfg->n_kv_heads == 0, "sk_lm_create: n_heads must be a multiple of n_kv_heads");
   SK_REQUIRE(cfg->vocab_size > 0 && cfg->vocab_size <= (1 << 20),
              "sk_lm_create: vocab_size must be in [1, 2^20] (unit vocabularies are ~502, interleaved text+unit ones ~152 k)");
@@ -313,7 +303,6 @@ int sk_lm_create(const SkLmConfig* cfg, SkLm** out) {
   lm->V = cfg->vocab_size;
   lm->Vp = (cfg->vocab_size + 63) / 64 * 64;
   lm->qkv_dim = (lm->H + 2 * lm->KVH) * lm->hd;
-  if (const char* e = getenv("SK_ATTN_TC")) lm->attn_tc = atoi(e);
   lm->lo.resize(lm->L);
   for (int l = 0; l < lm->L; ++l) {
     const std::string p = "layers." + std::to_string(l) + ".";
@@ -331,17 +320,43 @@ int sk_lm_create(const SkLmConfig* cfg, SkLm** out) {
   lm->off_head = cfg->tie_embeddings ? lm->off_embed : add_tensor(lm, "lm_head", lm->Vp, lm->d);
   SK_REQUIRE(lm->H * lm->hd == lm->d, "sk_lm_create: n_heads*head_dim must equal hidden");
 
-  // gradient-norm chunk tables
+  // gradient-norm chunk tables.  torch.nn.utils.clip_grad_norm_ takes one norm per PARAMETER (rounded to bf16 on bf16
+  // gradients), and HF keeps q/k/v and gate/up as separate parameters: a norm group here is one HF parameter, i.e. a
+  // list of element ranges of the flat buffer (q, k, v are row ranges of wqkv / bqkv; gate and up alternate in 128-row
+  // blocks of wgu).  Chunks are listed group by group, so a group is a contiguous run of the chunk table.
   std::vector<long> cs;
   std::vector<int> cl, tb;
-  for (const TensorDesc& t : lm->tensors) {
-    tb.push_back((int)cs.size());
-    const int64_t n = (int64_t)t.rows * t.cols;
+  auto add_range = [&](int64_t off, int64_t n) {
     for (int64_t o = 0; o < n; o += GN_CHUNK) {
-      cs.push_back((long)(t.off + o));
+      cs.push_back((long)(off + o));
       cl.push_back((int)((n - o) < GN_CHUNK ? (n - o) : GN_CHUNK));
     }
+  };
+  auto begin_group = [&]() { tb.push_back((int)cs.size()); };
+  const int64_t qd = (int64_t)lm->H * lm->hd, kvd = (int64_t)lm->KVH * lm->hd;
+  for (int l = 0; l < lm->L; ++l) {
+    const LayerOff& o = lm->lo[l];
+    begin_group(); add_range(o.ln1, lm->d);
+    begin_group(); add_range(o.wqkv, qd * lm->d);
+    begin_group(); add_range(o.wqkv + qd * lm->d, kvd * lm->d);
+    begin_group(); add_range(o.wqkv + (qd + kvd) * lm->d, kvd * lm->d);
+    if (cfg->qkv_bias) {
+      begin_group(); add_range(o.bqkv, qd);
+      begin_group(); add_range(o.bqkv + qd, kvd);
+      begin_group(); add_range(o.bqkv + qd + kvd, kvd);
+    }
+    begin_group(); add_range(o.wo, (int64_t)lm->d * lm->d);
+    begin_group(); add_range(o.ln2, lm->d);
+    for (int half = 0; half < 2; ++half) {   // gate, then up
+      begin_group();
+      for (int b = 0; b < lm->F / 128; ++b) add_range(o.wgu + ((int64_t)b * 256 + half * 128) * lm->d, (int64_t)128 * lm->d);
+    }
+    begin_group(); add_range(o.wd, (int64_t)lm->d * lm->F);
   }
+  begin_group(); add_range(lm->off_final_norm, lm->d);
+  begin_group(); add_range(lm->off_embed, (int64_t)lm->Vp * lm->d);
+  if (!cfg->tie_embeddings) { begin_group(); add_range(lm->off_head, (int64_t)lm->Vp * lm->d); }
+  lm->n_norm_groups = (int)tb.size();
   tb.push_back((int)cs.size());
   lm->n_chunks = (int)cs.size();
   SK_CUDA_CHECK(cudaMalloc(&lm->d_chunk_start, cs.size() * sizeof(long)));
@@ -476,10 +491,23 @@ int sk_lm_optimizer_step(SkLm* lm, void* exp_avg, void* exp_avg_sq, float lr, fl
   cudaStream_t s = (cudaStream_t)stream;
   sk_prof_begin(2, s);
   SK_TRY(sk_gradnorm_launch(lm->grads, lm->d_chunk_start, lm->d_chunk_len, lm->n_chunks, lm->d_tensor_chunk_begin,
-                            (int)lm->tensors.size(), lm->d_chunk_partial, max_grad_norm, emulate_bf16_norm, stats, s));
-  const int rc = sk_adamw_launch(lm->params, lm->grads, reinterpret_cast<bf16*>(exp_avg),
-                                 reinterpret_cast<bf16*>(exp_avg_sq), lm->n_params, lr, beta1, beta2, eps, weight_decay,
-                                 step, stats, s);
+                            lm->n_norm_groups, lm->d_chunk_partial, max_grad_norm, emulate_bf16_norm, stats, s));
+  int rc = 0;
+  if (weight_decay == 0.0f) {
+    rc = sk_adamw_launch(lm->params, lm->grads, reinterpret_cast<bf16*>(exp_avg), reinterpret_cast<bf16*>(exp_avg_sq),
+                         lm->n_params, lr, beta1, beta2, eps, 0.0f, step, stats, s);
+  } else {
+    // HF Trainer's decay groups (HF:trainer.py get_decay_parameter_names): biases and norm weights are NOT decayed.
+    // Non-default configuration (config/training_args/default.yaml has no weight_decay): one launch per tensor.
+    for (const TensorDesc& t : lm->tensors) {
+      const bool no_decay = t.rows == 1;   // ln1 / ln2 / final_norm / bqkv are the [1, n] tensors of the layout
+      const int64_t n = (((int64_t)t.rows * t.cols + ALIGN_ELEMS - 1) / ALIGN_ELEMS) * ALIGN_ELEMS;
+      rc = sk_adamw_launch(lm->params + t.off, lm->grads + t.off, reinterpret_cast<bf16*>(exp_avg) + t.off,
+                           reinterpret_cast<bf16*>(exp_avg_sq) + t.off, n, lr, beta1, beta2, eps,
+                           no_decay ? 0.0f : weight_decay, step, stats, s);
+      if (rc) break;
+    }
+  }
   sk_prof_end(s);
   return rc;
 }

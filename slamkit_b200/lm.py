@@ -142,52 +142,64 @@ class B200UnitLM:
             else:
                 t.copy_((torch.randn((r, c), generator=g) * std).to(torch.bfloat16))
 
-    def _hf_map(self) -> Iterator[Tuple[str, str, int, int]]:
-        """(flat tensor name, HF parameter name, row offset inside the flat tensor, n rows)."""
+    def _hf_map(self) -> Iterator[Tuple[str, str, List[Tuple[int, int, int]]]]:
+        """(flat tensor name, HF parameter name, [(row in the flat tensor, row in the HF tensor, n rows), ...]).
+
+        q/k/v are row ranges of the fused `wqkv` / `bqkv`.  gate_proj and up_proj share `wgu` in 128-row blocks --
+        flat rows [256b, 256b+128) = gate rows [128b, 128b+128), flat rows [256b+128, 256b+256) = the same up rows -- so
+        that one 256-column GEMM tile holds gate AND up of the same hidden units and SwiGLU runs in the GEMM epilogue."""
         cfg = self.config
         q, kv = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
+        nb = cfg.ffn // 128
         for l in range(cfg.n_layers):
             p, h = f"layers.{l}.", f"lm.model.layers.{l}."
-            yield p + "ln1", h + "input_layernorm.weight", 0, 1
-            yield p + "wqkv", h + "self_attn.q_proj.weight", 0, q
-            yield p + "wqkv", h + "self_attn.k_proj.weight", q, kv
-            yield p + "wqkv", h + "self_attn.v_proj.weight", q + kv, kv
-            yield p + "bqkv", h + "self_attn.q_proj.bias", 0, q
-            yield p + "bqkv", h + "self_attn.k_proj.bias", q, kv
-            yield p + "bqkv", h + "self_attn.v_proj.bias", q + kv, kv
-            yield p + "wo", h + "self_attn.o_proj.weight", 0, cfg.hidden
-            yield p + "ln2", h + "post_attention_layernorm.weight", 0, 1
-            yield p + "wgu", h + "mlp.gate_proj.weight", 0, cfg.ffn
-            yield p + "wgu", h + "mlp.up_proj.weight", cfg.ffn, cfg.ffn
-            yield p + "wd", h + "mlp.down_proj.weight", 0, cfg.hidden
-        yield "final_norm", "lm.model.norm.weight", 0, 1
-        yield "embed", "lm.model.embed_tokens.weight", 0, cfg.vocab_size
+            yield p + "ln1", h + "input_layernorm.weight", [(0, 0, 1)]
+            yield p + "wqkv", h + "self_attn.q_proj.weight", [(0, 0, q)]
+            yield p + "wqkv", h + "self_attn.k_proj.weight", [(q, 0, kv)]
+            yield p + "wqkv", h + "self_attn.v_proj.weight", [(q + kv, 0, kv)]
+            if cfg.qkv_bias:
+                yield p + "bqkv", h + "self_attn.q_proj.bias", [(0, 0, q)]
+                yield p + "bqkv", h + "self_attn.k_proj.bias", [(q, 0, kv)]
+                yield p + "bqkv", h + "self_attn.v_proj.bias", [(q + kv, 0, kv)]
+            yield p + "wo", h + "self_attn.o_proj.weight", [(0, 0, cfg.hidden)]
+            yield p + "ln2", h + "post_attention_layernorm.weight", [(0, 0, 1)]
+            yield p + "wgu", h + "mlp.gate_proj.weight", [(256 * b, 128 * b, 128) for b in range(nb)]
+            yield p + "wgu", h + "mlp.up_proj.weight", [(256 * b + 128, 128 * b, 128) for b in range(nb)]
+            yield p + "wd", h + "mlp.down_proj.weight", [(0, 0, cfg.hidden)]
+        yield "final_norm", "lm.model.norm.weight", [(0, 0, 1)]
+        yield "embed", "lm.model.embed_tokens.weight", [(0, 0, cfg.vocab_size)]
         if not cfg.tie_embeddings:
-            yield "lm_head", "lm.lm_head.weight", 0, cfg.vocab_size
+            yield "lm_head", "lm.lm_head.weight", [(0, 0, cfg.vocab_size)]
+
+    def _flat_rows(self, flat: str, grad: bool) -> torch.Tensor:
+        """The flat tensor as a [rows, cols] matrix; 1-row tensors (norm weights, the fused bias) as a column so that
+        the segment rows of `_hf_map` index elements."""
+        t = self.tensor(flat, grad=grad)
+        return t.view(-1, 1) if t.shape[0] == 1 else t
 
     def load_hf_state_dict(self, sd: Dict[str, torch.Tensor], grads: bool = False) -> None:
         """Load parameters named as in `UnitLM.state_dict()` (prefix `lm.`, slamkit/model/unit_lm.py:87)."""
-        for flat, hf, row0, nrows in self._hf_map():
-            src = sd[hf]
-            dst = self.tensor(flat, grad=grads)
-            if flat.endswith("bqkv") or src.dim() == 1:
-                if flat.endswith("bqkv"):
-                    dst.view(-1)[row0:row0 + nrows].copy_(src.to(torch.bfloat16))
-                else:
-                    dst.view(-1).copy_(src.to(torch.bfloat16))
-            else:
-                dst[row0:row0 + nrows].copy_(src.to(torch.bfloat16))
+        for flat, hf, segs in self._hf_map():
+            src = sd[hf].to(torch.bfloat16)
+            dst = self._flat_rows(flat, grads)
+            if src.dim() == 1:
+                src = src.view(-1, 1)
+            if segs == [(0, 0, 1)]:                       # whole norm weight
+                dst.view(-1).copy_(src.view(-1))
+                continue
+            for f0, h0, n in segs:
+                dst[f0:f0 + n].copy_(src[h0:h0 + n])
 
     def state_dict_hf(self, grads: bool = False) -> Dict[str, torch.Tensor]:
         out = {}
-        for flat, hf, row0, nrows in self._hf_map():
-            t = self.tensor(flat, grad=grads)
-            if flat.endswith("bqkv"):
-                out[hf] = t.view(-1)[row0:row0 + nrows].clone()
-            elif t.shape[0] == 1:
+        for flat, hf, segs in self._hf_map():
+            t = self._flat_rows(flat, grads)
+            if segs == [(0, 0, 1)]:
                 out[hf] = t.view(-1).clone()
-            else:
-                out[hf] = t[row0:row0 + nrows].clone()
+                continue
+            parts = [t[f0:f0 + n] for f0, h0, n in segs]    # segments are listed in HF row order
+            v = torch.cat(parts, dim=0) if len(parts) > 1 else parts[0].clone()
+            out[hf] = v.view(-1) if flat.endswith("bqkv") else v
         if self.config.tie_embeddings:
             out["lm.lm_head.weight"] = out["lm.model.embed_tokens.weight"]
         return out

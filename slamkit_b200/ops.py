@@ -120,8 +120,50 @@ def rope_(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, T: int, n_rot
     lib = L.require_cuda()
     M = qkv.shape[0]
     L.check(lib.sk_rope(L.ptr(qkv), L.ptr(cos), L.ptr(sin), L.ptr(pos_ids), M, T, qkv.stride(0), n_rot_heads, head_dim,
-                        int(inverse), L.stream_ptr()))
+                        int(inverse), cos.shape[0], L.stream_ptr()))
     return qkv
+
+
+def block_gate_up(w_gate: torch.Tensor, w_up: torch.Tensor) -> torch.Tensor:
+    """[F, K] gate / up weights (or [M, F] activations, transposed use) -> the [2F, K] 128-row block layout of the fused
+    SwiGLU linears: rows [256b, 256b+128) = gate rows [128b, 128b+128), rows [256b+128, 256b+256) = up rows."""
+    F = w_gate.shape[0]
+    assert F % 128 == 0 and w_up.shape == w_gate.shape
+    g = w_gate.view(F // 128, 128, -1)
+    u = w_up.view(F // 128, 128, -1)
+    return torch.stack([g, u], dim=1).reshape(2 * F, -1).contiguous()
+
+
+def linear_swiglu_fwd(x: torch.Tensor, w_gu_blocked: torch.Tensor):
+    """-> (gu [M, 2F] in block layout, act [M, F])"""
+    lib = L.require_cuda()
+    M, K = x.shape
+    F = w_gu_blocked.shape[0] // 2
+    gu = torch.empty((M, 2 * F), device=x.device, dtype=torch.bfloat16)
+    act = torch.empty((M, F), device=x.device, dtype=torch.bfloat16)
+    L.check(lib.sk_linear_swiglu_fwd(M, F, K, L.ptr(x), L.ptr(w_gu_blocked), L.ptr(gu), L.ptr(act), L.stream_ptr()))
+    return gu, act
+
+
+def linear_swiglu_bwd(dy: torch.Tensor, w_down: torch.Tensor, gu_blocked: torch.Tensor) -> torch.Tensor:
+    """dy [M, N], w_down [N, F], gu [M, 2F] (block layout) -> d_gu [M, 2F] (block layout)"""
+    lib = L.require_cuda()
+    M, N = dy.shape
+    F = w_down.shape[1]
+    dgu = torch.empty((M, 2 * F), device=dy.device, dtype=torch.bfloat16)
+    L.check(lib.sk_linear_swiglu_bwd(M, N, F, L.ptr(dy), L.ptr(w_down), L.ptr(gu_blocked), L.ptr(dgu), L.stream_ptr()))
+    return dgu
+
+
+def linear_rope(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cos: torch.Tensor, sin: torch.Tensor, T: int,
+                rope_cols: int, pos_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = L.require_cuda()
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+    L.check(lib.sk_linear_rope(M, N, K, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(out), L.ptr(cos), L.ptr(sin), L.ptr(pos_ids),
+                               T, rope_cols, cos.shape[0], L.stream_ptr()))
+    return out
 
 
 def swiglu_fwd(gu: torch.Tensor) -> torch.Tensor:

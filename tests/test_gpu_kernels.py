@@ -213,6 +213,58 @@ def test_swiglu_fwd_bwd():
     assert rel_err(dgu[:, F:], uf.grad) < 6e-3
 
 
+def _unblock(x_blocked, F):
+    """[M, 2F] in [128 gate | 128 up] column blocks -> (gate [M, F], up [M, F])"""
+    v = x_blocked.view(x_blocked.shape[0], F // 128, 2, 128)
+    return v[:, :, 0].reshape(-1, F), v[:, :, 1].reshape(-1, F)
+
+
+@pytest.mark.parametrize("M,F,K", [(300, 256, 128), (1000, 4864, 896), (8192, 4864, 896), (130, 384, 200)])
+def test_linear_swiglu_fused_matches_unfused_chain(M, F, K):
+    """gate/up GEMM with SwiGLU in the epilogue == plain GEMM followed by the swiglu kernel, bit for bit; the fused
+    backward (d_gu from dy * W_down without writing d_act) == dgrad GEMM followed by the swiglu backward kernel."""
+    from slamkit_b200 import ops
+    x, wg, wu = _randn(M, K, seed=1).to(DEV), _randn(F, K, seed=2, scale=0.05).to(DEV), _randn(F, K, seed=3, scale=0.05).to(DEV)
+    gu_b, act = ops.linear_swiglu_fwd(x, ops.block_gate_up(wg, wu))
+    gu_ref = ops.gemm(x, torch.cat([wg, wu], 0))                 # [M, 2F] = [gate | up]
+    g, u = _unblock(gu_b, F)
+    assert torch.equal(g, gu_ref[:, :F]) and torch.equal(u, gu_ref[:, F:])
+    assert torch.equal(act, ops.swiglu_fwd(gu_ref))
+    ref = torch.nn.functional.silu(gu_ref[:, :F]) * gu_ref[:, F:]        # bf16 ops, like HF
+    assert rel_err(act.cpu(), ref.cpu()) < 2e-3
+    # backward
+    N = K
+    dy, wd = _randn(M, N, seed=4).to(DEV), _randn(N, F, seed=5, scale=0.05).to(DEV)
+    dgu_b = ops.linear_swiglu_bwd(dy, wd, gu_b)
+    dact = ops.gemm(dy, wd, b_mn=True)
+    dgu_ref = ops.swiglu_bwd(gu_ref, dact)
+    dg, du = _unblock(dgu_b, F)
+    assert torch.equal(dg, dgu_ref[:, :F]) and torch.equal(du, dgu_ref[:, F:])
+
+
+@pytest.mark.parametrize("M,T,H,KVH,K,packed", [(200, 100, 3, 1, 128, False), (2048, 1024, 14, 2, 896, False), (512, 256, 4, 2, 256, True)])
+def test_linear_rope_fused_matches_unfused_chain(M, T, H, KVH, K, packed):
+    """QKV projection with bias + RoPE in the epilogue == GEMM(+bias) followed by the rope kernel, bit for bit."""
+    from slamkit_b200 import ops
+    from slamkit_b200.lm import rope_tables
+    hd = 64
+    N = (H + 2 * KVH) * hd
+    x, w, b = _randn(M, K, seed=1).to(DEV), _randn(N, K, seed=2, scale=0.05).to(DEV), _randn(N, seed=3).to(DEV)
+    cos, sin = rope_tables(10000.0, hd, 1024)
+    cos, sin = cos.to(DEV), sin.to(DEV)
+    pos = None
+    if packed:
+        g = torch.Generator().manual_seed(7)
+        pos = torch.cat([torch.arange(n) for n in (100, 156, 200, 56)]).to(torch.int32).to(DEV)
+        assert pos.numel() == M
+    out = ops.linear_rope(x, w, b, cos, sin, T, (H + KVH) * hd, pos_ids=pos)
+    ref = ops.rope_(ops.gemm(x, w, bias=b), cos, sin, T, H + KVH, hd, pos_ids=pos)
+    assert torch.equal(out, ref)
+    plain = ops.gemm(x, w, bias=b)
+    assert torch.equal(out[:, (H + KVH) * hd:], plain[:, (H + KVH) * hd:])      # v heads untouched
+    assert not torch.equal(out[:, :64], plain[:, :64])
+
+
 @pytest.mark.parametrize("num_items", [0.0, 777.0])
 def test_cross_entropy_fwd_bwd(num_items):
     from slamkit_b200 import ops
