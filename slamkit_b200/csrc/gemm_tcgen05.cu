@@ -1,11 +1,15 @@
 // tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T (+bias[N]) (+residual[M,N]),  bf16 in, fp32 accumulate
 // in TMEM, bf16 (or fp32) out.
 //
-// One persistent CTA per SM, 6 warps, warp-specialised:
+// One persistent CTA per SM, 10 warps, warp-specialised:
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      MMA issuer     (one lane issues tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction;
 //                               tcgen05.commit frees smem slots and publishes accumulators)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b.x32 from TMEM -> bias/residual -> 64 B per thread row stores)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b.x32 from TMEM -> bias / residual / fused element-wise op -> swizzled
+//                               smem -> TMA store).  Two warps per TMEM lane quadrant, each owning one half of the
+//                               tile's columns: with K = 896 (14 k-blocks per tile) the mainloop of a tile lasts ~6 us,
+//                               and a one-warp-per-quadrant epilogue (a single warp per scheduler, latency-bound) took
+//                               longer than that as soon as it did more than convert-and-store.
 // Accumulators are double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Operand majors.  "K-major" = the contraction index is contiguous in memory (A row-major [M,K], B row-major [N,K]).
@@ -27,7 +31,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+
 
 struct GemmParams {
   int M, N, K;          // M = rows per batch item when batch > 1
@@ -72,8 +76,9 @@ struct GemmParams {
   int rope_T, rope_cols, rope_maxpos;
 };
 
-template <int BN>
+template <int BN, int EW = 4>
 struct GemmCfg {
+  static constexpr int THREADS = 64 + 32 * EW;              // TMA warp, MMA warp, EW epilogue warps
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_ATOMS = (BN + 63) / 64;            // MN-major B is fetched in 64-column atoms
   static constexpr int B_BYTES = B_ATOMS * 64 * BK * 2;
@@ -81,7 +86,7 @@ struct GemmCfg {
   static constexpr int STAGES = (BN > 128) ? 4 : (BN > 64 ? 6 : 8);
   static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int STAGING_BYTES = 4 * 2 * 4096;  // per epilogue warp: 2 x (32 rows x 128 B) TMA-store buffers
+  static constexpr int STAGING_BYTES = 4 * 2 * 4096;  // (32 rows x 128 B) TMA-store buffers: 2 per warp (EW = 4) or 1 (EW = 8)
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 };
@@ -264,40 +269,33 @@ SK_DEVINL void epi_residual(float (&v)[8], const GemmParams& p, size_t row, int 
 constexpr int SK_SLOT_FLOATS = BM * 256;
 SK_DEVINL size_t sk_slot_off(int chunk, int j4, int row_in_tile) { return ((size_t)(chunk * 8 + j4) * BM + row_in_tile) * 4; }
 
-// add the partial tiles of n following groups (CTA first_cta, first_cta + G, ...) to the 32 accumulator columns in r;
-// loads of two partials are in flight together, the additions keep the group order
+// add the partial tiles of n following groups (CTA first_cta, first_cta + G, ...) to the 32 accumulator columns in r, in
+// group order (deterministic).  One partial (8 x float4 per thread) is in flight at a time: with 8 epilogue warps a thread
+// has 168 registers, and the two-deep version spilled.
 SK_DEVINL void sk_fixup_add(uint32_t (&r)[32], const float* ws, int chunk, int row_in_tile, int first_cta, int G, int n) {
-  for (int c0 = 0; c0 < n; c0 += 2) {
-    float4 a[2][8];
+  for (int c0 = 0; c0 < n; ++c0) {
+    const float* slot = ws + (size_t)(first_cta + c0 * G) * SK_SLOT_FLOATS;
+    float4 a[8];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (c0 + u < n) {
-        const float* slot = ws + (size_t)(first_cta + (c0 + u) * G) * SK_SLOT_FLOATS;
+    for (int j = 0; j < 8; ++j) a[j] = __ldcg(reinterpret_cast<const float4*>(slot + sk_slot_off(chunk, j, row_in_tile)));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[u][j] = __ldcg(reinterpret_cast<const float4*>(slot + sk_slot_off(chunk, j, row_in_tile)));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (c0 + u < n) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + a[u][j].x);
-          r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + a[u][j].y);
-          r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + a[u][j].z);
-          r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + a[u][j].w);
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + a[j].x);
+      r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + a[j].y);
+      r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + a[j].z);
+      r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + a[j].w);
     }
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool SK>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, bool SK, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EW>;
+  static_assert(EW == 4 || (EW == 8 && BN == 256 && !SK), "8 epilogue warps: plain 256-wide tiles only");
+  constexpr int CS = EW / 4;          // column split: epilogue warps per TMEM lane quadrant
   griddep_launch();                 // the next kernel on the stream may start its own prologue now
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -328,7 +326,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), EW);
     }
     fence_mbar_init();
   }
@@ -434,12 +432,133 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===== epilogue (warps 2..5); TMEM lane quadrant = warp % 4 =====
+    // ===== epilogue (warps 2..9); TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;   // 0 when EW == 4
+    uint32_t store_cnt = 0;
     int as = 0;
     uint32_t aphase = 0;
-    uint32_t store_cnt = 0;
     WorkIter<SK> w(p, num_kb_total, kb_per_split, total_items);
+    if (!SK && p.tma_store && p.epi == 2) {
+      // ===== SwiGLU backward epilogue: acc = d_act; d_gate = bf16(bf16(d_act*u) * silu'(g)), d_up = bf16(d_act * bf16(silu(g)))
+      // The accumulator arrives one ROW per thread, but gu / d_gu must move with coalesced accesses (a thread walking
+      // its own row issues 32 scattered 16-byte requests per instruction: measured slower than the unfused kernels).
+      // So bf16(d_act) goes through the warp's swizzled staging buffer and is re-read in a (4 rows x 8 pieces of
+      // 16 bytes) arrangement -- lane = (row % 4, piece) -- in which every global load / store instruction covers
+      // four full 128-byte row segments.  The gu registers are refilled in place for the NEXT chunk (of this tile or of
+      // the CTA's next tile) as soon as they have been consumed, so a whole chunk of math -- and, across tiles, the wait
+      // for the accumulator -- hides the DRAM latency.  Products of two bf16 values rounded to bf16 are single packed
+      // HMUL2.BF16 (exact product, one rounding: the same value as rounding the fp32 product).
+      const int lpiece = lane & 7, lrsub = lane >> 3;
+      const uint32_t sX = staging_base + (uint32_t)(warp - 2) * (EW == 4 ? 8192u : 4096u);
+      constexpr int NCH = BN / 64 / CS;           // 64-column chunks per warp and tile
+      const int c_lo = chalf * NCH;
+      // byte offset of this lane's gate piece for (tile origin m0/n0, chunk c2, k = 0); rows advance by 4 per k
+      auto piece_off = [&](int bidx, int m0, int n0, int c2, size_t ld) -> size_t {
+        const int acol = n0 + c2 * 64;
+        const int gcol = (acol >> 7) * 256 + (acol & 127) + lpiece * 8;
+        return (((size_t)bidx * p.M + m0 + q * 32 + lrsub) * ld + gcol) * sizeof(bf16);
+      };
+      auto tile_of = [&](const WorkIter<SK>& it, int& bidx, int& m0, int& n0) {
+        bidx = it.tile / tiles_per_batch;
+        const int rr = it.tile - bidx * tiles_per_batch;
+        m0 = (rr / p.tiles_n) * BM;
+        n0 = (rr % p.tiles_n) * BN;
+      };
+      const size_t row4_in = (size_t)4 * p.ld_aux * sizeof(bf16), row4_out = (size_t)4 * p.ldc * sizeof(bf16);
+      uint4 gv[8], uv[8];
+      auto gu_load_k = [&](int k, const uint8_t* base, int m0, int n0, int c2) {
+        const int rin = m0 + q * 32 + 4 * k + lrsub;
+        if (rin < p.M && n0 + c2 * 64 < p.N) {
+          gv[k] = ldg128(base + k * row4_in);
+          uv[k] = ldg128(base + k * row4_in + 256);
+        } else {
+          gv[k] = make_uint4(0u, 0u, 0u, 0u);
+          uv[k] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      bool have = w.next();
+      if (have) {
+        int bidx, m0, n0;
+        tile_of(w, bidx, m0, n0);
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(p.aux) + piece_off(bidx, m0, n0, c_lo, (size_t)p.ld_aux);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gu_load_k(k, base, m0, n0, c_lo);
+      }
+      while (have) {
+        int bidx, m0, n0;
+        tile_of(w, bidx, m0, n0);
+        WorkIter<SK> wn = w;
+        const bool have_next = wn.next();
+        int nb = 0, nm0 = 0, nn0 = 0;
+        if (have_next) tile_of(wn, nb, nm0, nn0);
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * Cfg::ACC_STRIDE);
+#pragma unroll 1
+        for (int c2 = c_lo; c2 < c_lo + NCH; ++c2) {
+          const bool col_ok = n0 + c2 * 64 < p.N;
+          {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(taddr + c2 * 64, r0);
+            tmem_ld_32x32(taddr + c2 * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t* r = j < 4 ? r0 + 8 * j : r1 + 8 * (j - 4);
+              const uint32_t dst = sX + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                           "r"(pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]))),
+                           "r"(pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]))),
+                           "r"(pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]))),
+                           "r"(pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7])))
+                           : "memory");
+            }
+          }
+          __syncwarp();
+          // where the registers freed below are refilled from: the next chunk of this tile, or the first chunk of the next
+          const bool last = c2 + 1 == c_lo + NCH;
+          const bool refill = last ? have_next : true;
+          const int fm0 = last ? nm0 : m0, fn0 = last ? nn0 : n0, fc2 = last ? c_lo : c2 + 1;
+          const uint8_t* fbase = reinterpret_cast<const uint8_t*>(p.aux) + piece_off(last ? nb : bidx, fm0, fn0, fc2, (size_t)p.ld_aux);
+          uint8_t* obase = reinterpret_cast<uint8_t*>(p.C) + piece_off(bidx, m0, n0, c2, (size_t)p.ldc);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int rr2 = 4 * k + lrsub;
+            const uint32_t off = (uint32_t)rr2 * 128u + (uint32_t)((lpiece ^ (rr2 & 7)) << 4);
+            uint32_t dw[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dw[0]), "=r"(dw[1]), "=r"(dw[2]), "=r"(dw[3]) : "r"(sX + off));
+            const uint32_t gw[4] = {gv[k].x, gv[k].y, gv[k].z, gv[k].w}, uw[4] = {uv[k].x, uv[k].y, uv[k].z, uv[k].w};
+            if (refill) gu_load_k(k, fbase, fm0, fn0, fc2);
+            uint32_t og[4], ou[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 gf = unpack_bf16(gw[e]);
+              const float s0 = sigmoid_f(gf.x), s1 = sigmoid_f(gf.y);
+              const uint32_t sil2 = pack_bf16(gf.x * s0, gf.y * s1);                       // bf16(silu(g))
+              const float ds0 = s0 * (1.0f + gf.x * (1.0f - s0)), ds1 = s1 * (1.0f + gf.y * (1.0f - s1));
+              const bf162 d2 = *reinterpret_cast<const bf162*>(&dw[e]);
+              bf162 du2 = __hmul2(d2, *reinterpret_cast<const bf162*>(&uw[e]));             // bf16(d_act * u)
+              bf162 o2 = __hmul2(d2, *reinterpret_cast<const bf162*>(&sil2));              // d_up
+              const float2 duf = __bfloat1622float2(du2);
+              og[e] = pack_bf16(duf.x * ds0, duf.y * ds1);
+              ou[e] = *reinterpret_cast<uint32_t*>(&o2);
+            }
+            if (col_ok && m0 + q * 32 + rr2 < p.M) {
+              stg128(obase + k * row4_out, make_uint4(og[0], og[1], og[2], og[3]));
+              stg128(obase + k * row4_out + 256, make_uint4(ou[0], ou[1], ou[2], ou[3]));
+            }
+          }
+          __syncwarp();                              // all lanes are done reading sX before the next chunk overwrites it
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+        have = w.next();
+      }
+    } else
     while (w.next()) {
       const int split = w.split;
       const int bidx = w.tile / tiles_per_batch;
@@ -493,8 +612,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         // one 64-column x 32-row bf16 chunk: registers -> this warp's swizzled staging buffer -> TMA store at (col, rows)
         auto stage_store = [&](const CUtensorMap* map, const uint32_t (&pk)[32], int col) {
-          const uint32_t sbuf = staging_base + (uint32_t)(warp - 2) * 8192u + (store_cnt & 1u) * 4096u;
-          if (lane == 0) tma_store_wait_read<1>();
+          const uint32_t sbuf = staging_base + (EW == 4 ? (uint32_t)(warp - 2) * 8192u + (store_cnt & 1u) * 4096u : (uint32_t)(warp - 2) * 4096u);
+          if (lane == 0) {
+            if constexpr (EW == 4) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+          }
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -515,7 +636,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // ---- SwiGLU forward: tile columns [0,128) = gate, [128,256) = up of the same 128 hidden units ----
           if constexpr (BN == 256) {
 #pragma unroll 1
-            for (int i = 0; i < 2; ++i) {
+#pragma unroll 1
+            for (int i = chalf * (2 / CS); i < (chalf + 1) * (2 / CS); ++i) {   // 64 gate columns, the matching up and act columns
               uint32_t gpk[32], upk[32];
               {
                 uint32_t r0[32], r1[32];
@@ -550,45 +672,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               stage_store(&tmAux, gpk, (n0 >> 1) + i * 64);
             }
           }
-        } else if (!SK && p.tma_store && p.epi == 2) {
-          // ---- SwiGLU backward: acc = d_act; d_gate = bf16(bf16(d_act*u) * silu'(g)), d_up = bf16(d_act * bf16(silu(g))) ----
-#pragma unroll 1
-          for (int c2 = 0; c2 < BN / 64; ++c2) {
-            const int acol = n0 + c2 * 64;
-            if (acol >= p.N) break;
-            const int gcol = (acol >> 7) * 256 + (acol & 127);   // gate columns in gu / d_gu; the up columns sit 128 further
-            uint32_t gw[32], uw[32];
-            if (row_ok) {
-              const bf16* gp = p.aux + row * (size_t)p.ld_aux + gcol;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint4 a = ldg128(gp + 8 * j), b = ldg128(gp + 128 + 8 * j);
-                gw[4 * j] = a.x; gw[4 * j + 1] = a.y; gw[4 * j + 2] = a.z; gw[4 * j + 3] = a.w;
-                uw[4 * j] = b.x; uw[4 * j + 1] = b.y; uw[4 * j + 2] = b.z; uw[4 * j + 3] = b.w;
-              }
-            } else {
-#pragma unroll
-              for (int t = 0; t < 32; ++t) gw[t] = uw[t] = 0u;
-            }
-            uint32_t r0[32], r1[32];
-            tmem_ld_32x32(taddr + c2 * 64, r0);
-            tmem_ld_32x32(taddr + c2 * 64 + 32, r1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int t = 0; t < 32; ++t) {
-              const float a0 = __uint_as_float(t < 16 ? r0[2 * t] : r1[2 * (t - 16)]);
-              const float a1 = __uint_as_float(t < 16 ? r0[2 * t + 1] : r1[2 * (t - 16) + 1]);
-              const float2 df = unpack_bf16(pack_bf16(a0, a1));        // bf16(d_act), what the unfused path stored
-              const float2 gf = unpack_bf16(gw[t]), uf = unpack_bf16(uw[t]);
-              const float s0 = sigmoid_f(gf.x), s1 = sigmoid_f(gf.y);
-              const float sil0 = bf16_round(gf.x * s0), sil1 = bf16_round(gf.y * s1);
-              const float ds0 = s0 * (1.0f + gf.x * (1.0f - s0)), ds1 = s1 * (1.0f + gf.y * (1.0f - s1));
-              gw[t] = pack_bf16(bf16_round(df.x * uf.x) * ds0, bf16_round(df.y * uf.y) * ds1);
-              uw[t] = pack_bf16(df.x * sil0, df.y * sil1);
-            }
-            stage_store(&tmC, gw, gcol);
-            stage_store(&tmC, uw, gcol + 128);
-          }
         } else if (!SK && p.tma_store && p.epi == 3) {
           // ---- bias + RoPE: a 64-column chunk is one attention head; element i pairs with element i + 32 ----
           uint32_t cw[16], sw[16];
@@ -604,7 +687,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
 #pragma unroll 1
-          for (int c2 = 0; c2 < BN / 64; ++c2) {
+          for (int c2 = chalf * (BN / 64 / CS); c2 < (chalf + 1) * (BN / 64 / CS); ++c2) {
             const int col64 = n0 + c2 * 64;
             if (col64 >= p.N) break;
             uint32_t r0[32], r1[32], pk[32];
@@ -644,9 +727,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else if (p.tma_store) {
           // coalesced path: TMEM -> registers -> 128B-swizzled smem (this warp's private 32-row buffer) -> TMA store
 #pragma unroll 1
-          for (int c2 = 0; c2 < BN / 64; ++c2) {
-            const uint32_t sbuf = staging_base + (uint32_t)(warp - 2) * 8192u + (store_cnt & 1u) * 4096u;
-            if (lane == 0) tma_store_wait_read<1>();
+          for (int c2 = chalf * (BN / 64 / CS); c2 < (chalf + 1) * (BN / 64 / CS); ++c2) {
+            const uint32_t sbuf = staging_base + (EW == 4 ? (uint32_t)(warp - 2) * 8192u + (store_cnt & 1u) * 4096u : (uint32_t)(warp - 2) * 4096u);
+            if (lane == 0) {
+              if constexpr (EW == 4) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+            }
             __syncwarp();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -682,7 +767,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         else
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = chalf * (BN / 32 / CS); c < (chalf + 1) * (BN / 32 / CS); ++c) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -849,17 +934,17 @@ int sk_make_tmap_3d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
 
 namespace {
 
-template <int BN, bool A_MN, bool B_MN, bool SK>
+template <int BN, bool A_MN, bool B_MN, bool SK, int EW = 4>
 int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EW>;
   static bool attr_set = false;
   if (!attr_set) {
-    SK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SK_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
   sk_prof_begin(0, stream);
-  cudaError_t lerr = sk_launch_pdl_if(p.pdl != 0, gemm_tcgen05_kernel<BN, A_MN, B_MN, SK>, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, stream,
+  cudaError_t lerr = sk_launch_pdl_if(p.pdl != 0, gemm_tcgen05_kernel<BN, A_MN, B_MN, SK, EW>, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, stream,
                                    tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   sk_prof_end(stream);
   SK_CUDA_CHECK(lerr);
@@ -867,12 +952,12 @@ int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream
   return 0;
 }
 
-template <int BN, bool SK>
+template <int BN, bool SK, int EW = 4>
 int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, SK>(tm, p, grid, s);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true, SK>(tm, p, grid, s);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false, SK>(tm, p, grid, s);
-  return launch_gemm<BN, true, true, SK>(tm, p, grid, s);
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, SK, EW>(tm, p, grid, s);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, SK, EW>(tm, p, grid, s);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, SK, EW>(tm, p, grid, s);
+  return launch_gemm<BN, true, true, SK, EW>(tm, p, grid, s);
 }
 
 // Relative cost of one 128 x BN tile (BN=256 == 100), measured on B200 (profiles/r01_gemm_bench.txt): narrow tiles
@@ -880,7 +965,7 @@ int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* tm, const GemmParams
 // (A 224-wide tile, which would fit N = 896 exactly, was measured no faster per tile than 256: r01_gemm_bench_v3.)
 inline int tile_cost(int bn) { return bn >= 256 ? 100 : (bn >= 128 ? 61 : 54); }
 
-constexpr size_t SK_FLAG_BYTES = 4096;   // tail of the scratch buffer: stream-K publish flags
+constexpr size_t SK_FLAG_BYTES = 4096;   // tail of the scratch buffer: stream-K publish flags ([CTA][TMEM lane quadrant])
 
 }  // namespace
 
@@ -1056,6 +1141,12 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
   if (p.sk_units > 0) {
     rc = dispatch_major<256, true>(g.a_mn, g.b_mn, tm, p, grid, stream);
   } else {
+    // 8 epilogue warps (two per TMEM lane quadrant) where the epilogue does real work per element; the plain
+    // convert-and-store epilogue is faster with 4 (fewer warps contending with the TMA / MMA issue threads)
+    static const int ew_env = [] { const char* e = getenv("SK_GEMM_EW"); return e ? atoi(e) : 0; }();
+    const bool ew8 = BN == 256 && p.tma_store && (ew_env == 8 || (ew_env == 0 && (g.epi == 2 || g.epi == 3)));
+    if (ew8) rc = dispatch_major<256, false, 8>(g.a_mn, g.b_mn, tm, p, grid, stream);
+    else
     switch (BN) {
       case 256: rc = dispatch_major<256, false>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
       case 128: rc = dispatch_major<128, false>(g.a_mn, g.b_mn, tm, p, grid, stream); break;
