@@ -5,7 +5,9 @@ descending-length batches (unit ids depend on batch composition, SURVEY.md §3.1
     python cli/extract_features.py data_path=<dir> ext=wav out_path=<features.jsonl> batch_size=16 \
         tokeniser=unit_hubert_25 tokeniser.feature_extractor_type=hubert_b200
 
-Under torchrun every rank takes whole batches round-robin and appends to `<out_path>.rank{r}`.
+Under torchrun every rank takes whole batches round-robin, writes `<out_path>.rank{r}`, and rank 0 merges them back into
+`<out_path>` in global batch order.  Files are decoded by `num_workers` threads ahead of the GPU and each
+batch's host-to-device copy runs on a copy stream from pinned memory (BatchPrefetcher).
 `+synthetic_weights=true` builds a seeded random mHuBERT-geometry extractor (no checkpoint reachable offline)."""
 import json
 import logging
@@ -47,11 +49,96 @@ def build_tokeniser(cfg, device: str, max_batch=None):
                              num_units=p.get("num_units") or fe_args["num_units"], load_fe=p.get("load_fe", True))
 
 
+class BatchPrefetcher:
+    """What `DataLoader(num_workers=4, collate_fn=pad_wav_collate)` + `.to(device)` do in the reference
+    (cli/extract_features.py:86-93), arranged for a GPU that finishes a 64 x 30 s batch in ~65 ms: `num_workers` threads
+    decode / resample the files of upcoming batches (the FLAC decoder and numpy release the GIL), a collector thread pads
+    each batch into one of `depth` PINNED host buffers and issues its host-to-device copy on a separate CUDA stream, and
+    the consumer receives device tensors whose copy overlapped the previous batch's kernels.  Order is the batch order."""
+
+    def __init__(self, batches, sample_rate: int, device: str, num_workers: int = 4, depth: int = 2):
+        import queue
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        self.batches, self.sr, self.dev = batches, sample_rate, torch.device(device)
+        self.pool = ThreadPoolExecutor(max_workers=max(1, num_workers))
+        self.q = queue.Queue(maxsize=depth)
+        self.free = queue.Queue()
+        for _ in range(depth + 1):
+            self.free.put(None)                      # pinned buffers are created lazily at the size of the largest batch seen
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            # decode futures run ahead of the collector by two batches
+            futs = [[self.pool.submit(load_audio, f, self.sr) for f, _ in b] for b in self.batches[:2]]
+            for i, batch in enumerate(self.batches):
+                if i + 2 < len(self.batches):
+                    futs.append([self.pool.submit(load_audio, f, self.sr) for f, _ in self.batches[i + 2]])
+                wavs = [ft.result() for ft in futs[i]]
+                futs[i] = None
+                lens = torch.tensor([len(w) for w in wavs])
+                B, S = len(wavs), int(lens.max())
+                buf = self.free.get()
+                if buf is None or buf.numel() < B * S:
+                    buf = torch.empty(B * S, dtype=torch.float32).pin_memory()
+                host = buf[:B * S].view(B, S)
+                host.zero_()
+                for r, w in enumerate(wavs):
+                    host[r, :len(w)] = w
+                with torch.cuda.stream(self.copy_stream):
+                    dev_wav = host.to(self.dev, non_blocking=True)
+                    dev_lens = lens.to(self.dev, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(self.copy_stream)
+                self.q.put((batch, dev_wav, dev_lens, ready, buf))
+            self.q.put(None)
+        except BaseException as e:                   # surface loader errors in the consumer
+            self.q.put(e)
+
+    def __iter__(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            batch, dev_wav, dev_lens, ready, buf = item
+            torch.cuda.current_stream().wait_event(ready)
+            dev_wav.record_stream(torch.cuda.current_stream())
+            dev_lens.record_stream(torch.cuda.current_stream())
+            yield batch, dev_wav, dev_lens
+            # the pinned buffer is reusable once its copy has executed; the event was recorded right after it
+            ready.synchronize()
+            self.free.put(buf)
+
+
+def merge_rank_files(out_path: str, world: int) -> None:
+    """Deterministic merge of the per-rank outputs: rank r wrote whole batches r, r + world, ... in order,
+    one json line per file; interleave them back into global batch order (= the single-process file order)."""
+    recs = [[json.loads(l) for l in open(f"{out_path}.rank{r}")] for r in range(world)]
+    n_batches = [json.load(open(f"{out_path}.rank{r}.batches")) for r in range(world)]
+    with open(out_path, "a+") as out:
+        pos = [0] * world
+        for bi in range(max(len(n) for n in n_batches)):
+            for r in range(world):
+                if bi < len(n_batches[r]):
+                    k = n_batches[r][bi]
+                    out.writelines(json.dumps(x) + "\n" for x in recs[r][pos[r]:pos[r] + k])
+                    pos[r] += k
+    for r in range(world):
+        os.remove(f"{out_path}.rank{r}")
+        os.remove(f"{out_path}.rank{r}.batches")
+
+
 def main(argv=None):
     cfg = load_config("extract_features", argv if argv is not None else sys.argv[1:])
     require(cfg, "data_path", "out_path")
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+    torch.cuda.set_device(device)
     files = [(f, audio_num_frames(f)) for f in iglob(os.path.join(cfg.data_path, f"**/*.{cfg.ext}"), recursive=True)]
     files.sort(key=lambda x: x[1], reverse=True)          # WavDataset: sort by duration, longest first
     if cfg.data_skip is not None:
@@ -61,22 +148,34 @@ def main(argv=None):
     tokeniser = build_tokeniser(cfg, device)
     out_path = cfg.out_path if world == 1 else f"{cfg.out_path}.rank{rank}"
     if os.path.exists(out_path):
-        logging.warning(f"{out_path} already exists. Appending to it.")
+        if world > 1:
+            os.remove(out_path)                           # rank files are scratch; the merged file keeps append semantics
+        else:
+            logging.warning(f"{out_path} already exists. Appending to it.")
     os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
     batches = [files[i:i + cfg.batch_size] for i in range(0, len(files), cfg.batch_size)]
+    mine = [b for bi, b in enumerate(batches) if bi % world == rank]      # whole batches round-robin (ids depend on batch composition)
+    sizes = []
     with open(out_path, "a+") as out_file:
-        for bi, batch in enumerate(batches):
-            if bi % world != rank:
-                continue
-            wavs = [load_audio(f, cfg.sample_rate) for f, _ in batch]
-            lens = torch.tensor([len(w) for w in wavs])
-            wav = torch.nn.utils.rnn.pad_sequence(wavs, batch_first=True, padding_value=0)
+        for batch, wav, lens in BatchPrefetcher(mine, cfg.sample_rate, device, num_workers=cfg.get("num_workers", 4) or 1):
             reps = tokeniser.audio_represent(wav, lens)
             lines = []
             for (f, _), rep in zip(batch, reps):
                 rec = {"units": list(rep["units"]), "duration": list(rep["duration"]), "file_name": f}
                 lines.append(json.dumps(rec) + "\n")
             out_file.writelines(lines)
+            sizes.append(len(batch))
+    if world > 1:
+        import torch.distributed as dist
+        json.dump(sizes, open(out_path + ".batches", "w"))
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")
+        dist.barrier()
+        if rank == 0:
+            merge_rank_files(cfg.out_path, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        return cfg.out_path
     return out_path
 
 

@@ -25,7 +25,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from cli.train import parse_run_time  # noqa: E402
-from slamkit_b200.config import load_config, require, to_container  # noqa: E402
+from slamkit_b200.config import load_config, require  # noqa: E402
 from slamkit_b200.dpo import collate_pairs, tokenize_row  # noqa: E402
 from slamkit_b200.tokeniser import B200UnitTokeniser  # noqa: E402
 
@@ -92,39 +92,45 @@ def main(argv=None):
     torch.cuda.set_device(local_rank)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from cli.train import build_model
     from slamkit_b200.dpo import B200DPOTrainer
-    from slamkit_b200.lm import B200UnitLM, LMConfig, cosine_with_min_lr
-    bs = ta.per_device_train_batch_size
+    from slamkit_b200.lm import B200UnitLM, cosine_with_min_lr
+    bs, ga = ta.per_device_train_batch_size, ta.get("gradient_accumulation_steps", 1)
     dev = f"cuda:{local_rank}"
 
     def build():
         if cfg.model.get("pretrained_model"):
             return B200UnitLM.from_pretrained(cfg.model.pretrained_model, device=dev, max_batch=2 * bs, max_seq=max_len)
-        try:
-            from slamkit_b200.integration import tlm_b200_from_cfg
-            return tlm_b200_from_cfg(to_container(cfg.model), device=dev, max_batch=2 * bs)
-        except Exception as e:   # offline: no base model -> seeded random init of the configured shape
-            logger.warning(f"base model unavailable ({type(e).__name__}); random init")
-            return B200UnitLM(LMConfig(vocab_size=cfg.model.config_args.vocab_size), device=dev, max_batch=2 * bs,
-                              max_seq=max_len, seed=0)
+        return build_model(cfg, dev, 2 * bs, max_len)     # same rules as cli/train.py: no silent random-init fallback
     policy, reference = build(), build()          # trl: the reference is a frozen copy of the initial policy
-    steps_per_epoch = max(1, math.ceil(len(pairs) / (bs * world)))
-    total = ta.get("max_steps") or int(steps_per_epoch * ta.num_train_epochs)
+    steps_per_epoch = max(1, math.ceil(len(pairs) / (bs * ga * world)))
+    total = ta.get("max_steps") or int(math.ceil(steps_per_epoch * ta.num_train_epochs))
     warmup = ta.get("warmup_steps", 0)
     min_lr = (ta.get("lr_scheduler_kwargs") or {}).get("min_lr", 0.0)
+    # data parallel as trl under accelerate DDP (reference cli/preference_alignment_train.py:56-65): every rank takes its
+    # own pairs, gradients are summed over ranks with the 1/world factor folded into the per-sequence weights
     trainer = B200DPOTrainer(policy, reference, beta=ta.get("beta", 0.1), lr=ta.learning_rate,
-                             max_grad_norm=ta.max_grad_norm, weight_decay=ta.get("weight_decay", 0.0))
+                             max_grad_norm=ta.max_grad_norm, weight_decay=ta.get("weight_decay", 0.0), grad_accum=ga)
     budget = parse_run_time(cfg.run_time) if cfg.get("run_time") is not None else None
     order = torch.randperm(len(pairs), generator=torch.Generator().manual_seed(ta.get("seed", 42))).tolist()
-    t0, cursor, log = time.time(), rank * bs, []
+    t0, cursor, log = time.time(), 0, []
     for step in range(1, total + 1):
-        batch = [pairs[order[(cursor + i) % len(order)]] for i in range(bs)]
-        cursor += bs * world
-        ids, labels = collate_pairs(batch, tok.pad_token_id)
+        mids, mlabs = [], []
+        for _ in range(ga):
+            batch = [pairs[order[(cursor + rank * bs + i) % len(order)]] for i in range(bs)]
+            cursor += bs * world
+            ids, labels = collate_pairs(batch, tok.pad_token_id)
+            mids.append(ids)
+            mlabs.append(labels)
         lr = cosine_with_min_lr(step - 1, base_lr=ta.learning_rate, min_lr=min_lr, warmup_steps=warmup, total_steps=total)
-        out = trainer.step(ids, labels, lr=lr)
+        out = trainer.step(mids, mlabs, lr=lr)
         if step % ta.get("logging_steps", 10) == 0 or step == total:
-            rec = {"step": step, "elapsed_s": time.time() - t0, **{k: float(v) for k, v in out.items() if torch.is_tensor(v) and v.numel() == 1}}
+            vals = {k: v.float().mean() for k, v in out.items() if torch.is_tensor(v)}
+            if world > 1:                                     # report the mean over ranks, as trl's gathered metrics
+                for v in vals.values():
+                    dist.all_reduce(v)
+                    v /= world
+            rec = {"step": step, "elapsed_s": time.time() - t0, **{k: float(v) for k, v in vals.items()}}
             log.append(rec)
             if rank == 0:
                 print(json.dumps(rec), flush=True)

@@ -72,7 +72,8 @@ int sk_linear_rope(int M, int N, int K, const void* x, const void* w, const void
 /* ---- causal-LM element-wise / reduction kernels (path (ii)) --------------------------------------------------- */
 /* Embedding lookup, HF:models/qwen2/modeling_qwen2.py:332-415 (embed_tokens). ids int64 [M]. */
 int sk_embed_fwd(const int64_t* ids, const void* table, void* out, int M, int D, int V, void* stream);
-/* dTable[ids[m]] += dx[m]; scratch: fp32 [Vpad*D]; accumulate=1 keeps the existing bf16 gradient. */
+/* dTable[ids[m]] += dx[m]; scratch: Vpad*D 64-bit words (2 floats each: the rows are summed in 64-bit fixed point, so
+ * the result does not depend on the order the atomics land in); accumulate=1 keeps the existing bf16 gradient. */
 int sk_embed_bwd(const int64_t* ids, const void* dx, float* scratch, void* dtable, int M, int D, int V, int Vpad,
                  int accumulate, void* stream);
 /* Qwen2RMSNorm, HF:models/qwen2/modeling_qwen2.py:249-262. rstd (fp32 [M]) may be NULL. */

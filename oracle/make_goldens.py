@@ -13,6 +13,7 @@ What is pinned:
                    block-diagonal causal 4-D mask: pins the oracle's `packed=True` path bit-exactly.
   tokeniser.npz    reference `UnitTokeniser` (load_fe=False) ids for the two example_data strings and the dedup of
                    example_data/features.jsonl (units/durations are already golden files of the reference).
+  lm_loglik.npz    reference `UnitLM.log_likelihood` (sum and mean forms) on a right-padded batch, seeded weights.
   hubert_tiny.npz  reference `HubertFeatureExtractor.extract` + `batch_cluster` (HF HubertModel, sklearn
                    KMeans.predict) on seeded weights: small mHuBERT-25Hz-geometry model, 2 ragged clips.
 """
@@ -175,6 +176,25 @@ def make_lm_packed_golden(out_path: str):
     print("lm packed golden: loss", out.loss.item(), "->", out_path)
 
 
+def make_loglik_golden(out_path: str):
+    """`UnitLM.log_likelihood` (slamkit/model/unit_lm.py:184-194) of the reference model on seeded weights: a right-padded
+    batch (pad id 0 is excluded from the sum), summed and mean forms.  What cli/eval.py's modelling metrics call."""
+    from oracle.lm_oracle import OracleLMConfig
+    ocfg = OracleLMConfig(vocab_size=502, hidden=128, n_layers=2, n_heads=2, n_kv_heads=1, head_dim=64, ffn=256)
+    model, _ = _reference_unit_lm(ocfg, 3)
+    model.eval()
+    g = torch.Generator().manual_seed(11)
+    tokens = torch.randint(2, 502, (3, 40), generator=g)
+    tokens[:, 0] = 1
+    tokens[1, 25:] = 0
+    tokens[2, 33:] = 0
+    ll_sum = model.log_likelihood(tokens.clone(), mean_nll=False)
+    ll_mean = model.log_likelihood(tokens.clone(), mean_nll=True)
+    np.savez_compressed(out_path, tokens=tokens.numpy(), ll_sum=ll_sum.float().numpy(), ll_mean=ll_mean.float().numpy(),
+                        seed_params=np.int64(3))
+    print("loglik golden:", ll_sum.tolist(), ll_mean.tolist(), "->", out_path)
+
+
 def make_tokeniser_golden(out_path: str):
     from slamkit.tokeniser.unit_tokeniser import UnitTokeniser
 
@@ -246,7 +266,9 @@ if __name__ == "__main__":
     sys.path.insert(0, REF)
     gd = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gd, exist_ok=True)
-    which = sys.argv[1:] or ["lm", "packed", "tokeniser", "hubert"]
+    which = sys.argv[1:] or ["lm", "packed", "loglik", "tokeniser", "hubert"]
+    if "loglik" in which:
+        make_loglik_golden(os.path.join(gd, "lm_loglik.npz"))
     if "lm" in which:
         make_lm_golden(os.path.join(gd, "lm_tiny.npz"))
     if "packed" in which:

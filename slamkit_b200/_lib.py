@@ -75,7 +75,7 @@ def load() -> C.CDLL:
         )
     lib = C.CDLL(LIB_PATH)
     lib.sk_last_error.restype = C.c_char_p
-    for name in ("sk_lm_param_count", "sk_lm_workspace_bytes", "sk_launch_count", "sk_hubert_param_count",
+    for name in ("sk_lm_param_count", "sk_lm_workspace_bytes", "sk_launch_count", "sk_hubert_param_count", "sk_hubert_prepared_bytes",
                  "sk_hubert_workspace_bytes", "sk_gemm_ws_bytes"):
         if hasattr(lib, name):
             getattr(lib, name).restype = C.c_int64

@@ -178,21 +178,41 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);       // S consumed: the next S MMA may overwrite it
+      // cmax: last 32-key group of this tile the warp's rows can see (warp-uniform).  On the causal diagonal tile
+      // (k0 == q0, BR == BC) the rows of TMEM quadrant q see groups 0..q-1 completely, group q up to their own index,
+      // and nothing of the groups behind: those are neither compared, nor exponentiated (62 % of a tile's MUFU work on
+      // average), they are written to P as zeros.
+      int cmax = 3;
       if (need_mask) {
+        if (CAUSAL && seg_start == nullptr && k0 == q0 && k0 + AT_BC <= T) {
+          cmax = q;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 4; ++c)
+            if (c == q) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int key = k0 + c * 32 + i;
-            if (key >= T || (CAUSAL && key > qrow) || key < lb) v[c][i] = 0xff800000u;  // -inf
-          }
+              for (int i = 0; i < 32; ++i)
+                if (i > lane) v[c][i] = 0xff800000u;  // -inf
+            }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int key = k0 + c * 32 + i;
+              if (key >= T || (CAUSAL && key > qrow) || key < lb) v[c][i] = 0xff800000u;  // -inf
+            }
+        }
       }
-      float mx = m_run;
+      // row max: independent chains (one per 32-key group) instead of one 128-long dependent chain
+      float mc[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < 4; ++c)
+        if (c <= cmax) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c][i]));
-      const float m_new = mx;
+          for (int i = 0; i < 32; i += 2)
+            mc[c] = fmaxf(mc[c], fmaxf(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])));
+        }
+      const float m_new = fmaxf(fmaxf(mc[0], mc[1]), fmaxf(mc[2], mc[3]));
       const float mb = (m_new == -INFINITY) ? 0.f : m_new * sl2;
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * sl2 - mb);
       // the P buffer (and O) are still being read by the previous PV MMA until o_done: wait before overwriting P
@@ -200,17 +220,25 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         mbar_wait(o_done, (j - 1) & 1);
         tc_fence_after();
       }
-      float rs0 = 0.f, rs1 = 0.f;
+      // p = 2^(s * scale*log2e - m * scale*log2e): packed FFMA2 for the argument, one MUFU.EX2 per element, packed FADD2
+      // row sums in four independent chains
+      const f32x2 sl22 = dup2(sl2), nmb2 = dup2(-mb);
+      f32x2 rsum[4] = {dup2(0.f), dup2(0.f), dup2(0.f), dup2(0.f)};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
+        if (c <= cmax) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), sl2, -mb));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, -mb));
-          rs0 += p0;
-          rs1 += p1;
-          pk[i] = pack_bf16(p0, p1);
+          for (int i = 0; i < 16; ++i) {
+            float x0, x1;
+            upk2(fma2(pk2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), sl22, nmb2), x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            rsum[i & 3] = add2(rsum[i & 3], pk2(p0, p1));
+            pk[i] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -221,8 +249,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
                        : "memory");
         }
       }
-      const float rs = rs0 + rs1;
-
+      float rs;
+      {
+        float a0, a1;
+        upk2(add2(add2(rsum[0], rsum[1]), add2(rsum[2], rsum[3])), a0, a1);
+        rs = a0 + a1;
+      }
       l_run = l_run * alpha + rs;
       m_run = m_new;
       // correction: rescale O when this row's max moved (skipped warp-wide when no lane needs it)
@@ -724,20 +756,38 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
       const bool need_mask = (CAUSAL && k0 + BQ_BC - 1 > q0) || (k0 + BQ_BC > T) || (q0 + AT_BR > T) || (k0 < lb);
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x0, x1;
-        upk2(fma2(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl22, nlse2), x0, x1);
-        float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-        if (need_mask) {
-          const int key = k0 + half * 32 + 2 * i;
-          if (!row_ok || key >= T || (CAUSAL && key > qrow) || key < lb) p0 = 0.f;
-          if (!row_ok || key + 1 >= T || (CAUSAL && key + 1 > qrow) || key + 1 < lb) p1 = 0.f;
+      // mask mode of this warp's 32 keys (warp-uniform): 0 all visible, 1 causal diagonal group (key index <= the row's
+      // lane), 2 all masked (nothing to compute: dS = 0), 3 general (sequence end / document bounds: per element)
+      int mode = 0;
+      if (need_mask) {
+        mode = 3;
+        if (CAUSAL && seg_start == nullptr && q0 + AT_BR <= T && k0 + BQ_BC <= T) {
+          const int g = ((k0 - q0) >> 5) + half;       // this warp's key group, in 32-key units from the tile's first row
+          mode = g < q ? 0 : (g == q ? 1 : 2);
         }
-        float d0, d1;
-        upk2(mul2(pk2(p0, p1), sub2(pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), del2)), d0, d1);
-        pk[i] = pack_bf16(d0, d1);
+      }
+      uint32_t pk[16];
+      if (mode == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x0, x1;
+          upk2(fma2(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl22, nlse2), x0, x1);
+          float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          if (mode == 1) {
+            if (2 * i > lane) p0 = 0.f;
+            if (2 * i + 1 > lane) p1 = 0.f;
+          } else if (mode == 3) {
+            const int key = k0 + half * 32 + 2 * i;
+            if (!row_ok || key >= T || (CAUSAL && key > qrow) || key < lb) p0 = 0.f;
+            if (!row_ok || key + 1 >= T || (CAUSAL && key + 1 > qrow) || key + 1 < lb) p1 = 0.f;
+          }
+          float d0, d1;
+          upk2(mul2(pk2(p0, p1), sub2(pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), del2)), d0, d1);
+          pk[i] = pack_bf16(d0, d1);
+        }
       }
       mbar_wait(ds_empty, (j & 1) ^ 1u);         // previous dQ MMA finished reading the dS buffer (the math above overlaps it)
 #pragma unroll
@@ -787,7 +837,7 @@ template <bool CAUSAL>
 __global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                         const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
-                        const float* __restrict__ delta, float* __restrict__ partial /*[B][H][T][128]*/, int T, int H,
+                        const float* __restrict__ delta, bf16* __restrict__ partial /*[B][H][T][128]*/, int T, int H,
                         int KVH, float scale, const int* __restrict__ seg_start, const int* __restrict__ seg_end) {
   griddep_launch();
   extern __shared__ uint8_t smem_raw[];
@@ -929,26 +979,48 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_empty);
       const bool need_mask = (CAUSAL && q0 < k0 + AT_BC) || (q0 + BK_BR > T) || (k0 + AT_BC > T) || seg_start != nullptr;
+      // mask mode of this warp's 32 queries against its 32 key rows (warp-uniform): 0 all visible, 1 causal diagonal
+      // group (key lane <= query index), 2 all masked (P^T = dS^T = 0, nothing to compute), 3 general (per element)
+      int mode = 0;
+      if (need_mask) {
+        mode = 3;
+        if (CAUSAL && seg_start == nullptr && q0 + BK_BR <= T && k0 + AT_BC <= T) {
+          const int gq = ((q0 - k0) >> 5) + half;      // this warp's query group, in 32-row units from the key tile's first row
+          mode = gq > q ? 0 : (gq == q ? 1 : 2);
+        }
+      }
       uint32_t pp[16], pd[16];
       // packed-pair math (two queries per instruction); dS'^T omits the 1/sqrt(d) factor, applied to dK in the epilogue
+      if (mode == 2) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int qi = half * 32 + 2 * e;
-        const f32x2 nl2 = *reinterpret_cast<const f32x2*>(st_lse + qi);
-        const f32x2 dl = *reinterpret_cast<const f32x2*>(st_lse + 64 + qi);
-        float x0, x1;
-        upk2(fma2(pk2(__uint_as_float(sv[2 * e]), __uint_as_float(sv[2 * e + 1])), sl22, nl2), x0, x1);
-        float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-        if (need_mask) {
-          const int qrow = q0 + qi;
-          const int2 sg = *reinterpret_cast<const int2*>(st_lse + 128 + qi);     // first visible key of the two queries
-          if (key >= T || qrow >= T || (CAUSAL && key > qrow) || key < sg.x) p0 = 0.f;
-          if (key >= T || qrow + 1 >= T || (CAUSAL && key > qrow + 1) || key < sg.y) p1 = 0.f;
+        for (int e = 0; e < 16; ++e) pp[e] = pd[e] = 0u;
+      } else {
+#pragma unroll
+        for (int e2 = 0; e2 < 8; ++e2) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int e = 2 * e2 + u;
+            const int qi = half * 32 + 2 * e;
+            const f32x2 nl2 = *reinterpret_cast<const f32x2*>(st_lse + qi);
+            const f32x2 dl = *reinterpret_cast<const f32x2*>(st_lse + 64 + qi);
+            float x0, x1;
+            upk2(fma2(pk2(__uint_as_float(sv[2 * e]), __uint_as_float(sv[2 * e + 1])), sl22, nl2), x0, x1);
+            float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            if (mode == 1) {
+              if (lane > 2 * e) p0 = 0.f;
+              if (lane > 2 * e + 1) p1 = 0.f;
+            } else if (mode == 3) {
+              const int qrow = q0 + qi;
+              const int2 sg = *reinterpret_cast<const int2*>(st_lse + 128 + qi);     // first visible key of the two queries
+              if (key >= T || qrow >= T || (CAUSAL && key > qrow) || key < sg.x) p0 = 0.f;
+              if (key >= T || qrow + 1 >= T || (CAUSAL && key > qrow + 1) || key < sg.y) p1 = 0.f;
+            }
+            pp[e] = pack_bf16(p0, p1);
+            float d0, d1;
+            upk2(mul2(pk2(p0, p1), sub2(pk2(__uint_as_float(dv[2 * e]), __uint_as_float(dv[2 * e + 1])), dl)), d0, d1);
+            pd[e] = pack_bf16(d0, d1);
+          }
         }
-        pp[e] = pack_bf16(p0, p1);
-        float d0, d1;
-        upk2(mul2(pk2(p0, p1), sub2(pk2(__uint_as_float(dv[2 * e]), __uint_as_float(dv[2 * e + 1])), dl)), d0, d1);
-        pd[e] = pack_bf16(d0, d1);
       }
       mbar_wait(pds_empty, (i & 1) ^ 1u);        // previous dV / dK MMAs finished reading P^T / dS^T (overlapped by the math)
 #pragma unroll
@@ -973,7 +1045,9 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       mbar_wait(acc_done, 0);
       tc_fence_after();
     }
-    float* pp = partial + (((size_t)b * H + h) * T + key) * 128;
+    // per-(query head) partials in bf16: the reference's autograd also rounds every expanded head's dK / dV to bf16
+    // before summing them over the GQA group (repeat_kv backward); half the bytes of fp32 partials
+    bf16* pp = partial + (((size_t)b * H + h) * T + key) * 128;
 #pragma unroll 1
     for (int c = half * 2; c < half * 2 + 2; ++c) {   // columns 0..63 = dK (TMEM 128..191), 64..127 = dV (192..255)
       uint32_t v[32];
@@ -987,10 +1061,12 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       if (key < T) {
         const float cs = c < 2 ? scale : 1.0f;     // dK columns carry the deferred 1/sqrt(d)
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          *reinterpret_cast<float4*>(pp + c * 32 + u * 4) =
-              make_float4(__uint_as_float(v[4 * u]) * cs, __uint_as_float(v[4 * u + 1]) * cs,
-                          __uint_as_float(v[4 * u + 2]) * cs, __uint_as_float(v[4 * u + 3]) * cs);
+        for (int u = 0; u < 4; ++u)
+          stg128(pp + c * 32 + u * 8,
+                 make_uint4(pack_bf16(__uint_as_float(v[8 * u]) * cs, __uint_as_float(v[8 * u + 1]) * cs),
+                            pack_bf16(__uint_as_float(v[8 * u + 2]) * cs, __uint_as_float(v[8 * u + 3]) * cs),
+                            pack_bf16(__uint_as_float(v[8 * u + 4]) * cs, __uint_as_float(v[8 * u + 5]) * cs),
+                            pack_bf16(__uint_as_float(v[8 * u + 6]) * cs, __uint_as_float(v[8 * u + 7]) * cs)));
       }
     }
   }
@@ -1003,7 +1079,7 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 }
 
 // dk / dv (bf16, column slices of the fused gradient buffer) = sum over the GQA group's query heads, fixed order
-__global__ void attn_tc_group_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ dk, bf16* __restrict__ dv,
+__global__ void attn_tc_group_reduce_kernel(const bf16* __restrict__ partial, bf16* __restrict__ dk, bf16* __restrict__ dv,
                                             int B, int T, int H, int KVH, int ldg) {
   griddep_launch();
   griddep_wait();
@@ -1017,10 +1093,14 @@ __global__ void attn_tc_group_reduce_kernel(const float* __restrict__ partial, b
     const int b = (int)(rt / ((long)T * KVH));
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int j = 0; j < group; ++j) {
-      const float* src = partial + (((size_t)b * H + gg * group + j) * T + t) * 128 + c8 * 8;
-      const float4 a = *reinterpret_cast<const float4*>(src), c = *reinterpret_cast<const float4*>(src + 4);
-      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-      acc[4] += c.x; acc[5] += c.y; acc[6] += c.z; acc[7] += c.w;
+      const uint4 a = ldg128_stream(partial + (((size_t)b * H + gg * group + j) * T + t) * 128 + c8 * 8);
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16(w[k]);
+        acc[2 * k] += f.x;
+        acc[2 * k + 1] += f.y;
+      }
     }
     bf16* dst = (c8 < 8 ? dk : dv) + ((size_t)b * T + t) * ldg + gg * 64 + (c8 & 7) * 8;
     stg128(dst, make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
@@ -1033,7 +1113,7 @@ __global__ void attn_tc_group_reduce_kernel(const float* __restrict__ partial, b
 // Backward launcher.  qkv / dqkv share the fused [B*T, ld] layout; delta fp32 [B,H,T] and partial fp32 [B,H,T,128] are
 // caller-provided scratch (delta is filled here).
 int sk_attn_delta_launch(const bf16* o, const bf16* d_o, float* delta, int B, int T, int H, int ldo, cudaStream_t s);
-int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse, float* delta, float* partial,
+int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse, float* delta, float* partial_f,
                           bf16* dqkv, int B, int T, int H, int KVH, int ld, int ldo, int ldg, int causal, float scale,
                           cudaStream_t s, const int* seg_start, const int* seg_end) {
   SK_REQUIRE((seg_start == nullptr) == (seg_end == nullptr), "attn_tc_bwd: seg_start and seg_end go together");
@@ -1053,6 +1133,7 @@ int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const
     SK_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_dkdv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKDV_SMEM));
     init = true;
   }
+  bf16* partial = reinterpret_cast<bf16*>(partial_f);   // bf16 [B,H,T,128]: uses the first half of the caller's fp32-sized scratch
   SK_TRY_RC(sk_attn_delta_launch(o, d_o, delta, B, T, H, ldo, s));
   sk_prof_begin(1, s);
   dim3 g1(H, B, (T + AT_BC - 1) / AT_BC), g2(H, B, (T + AT_BR - 1) / AT_BR);

@@ -75,6 +75,9 @@ extern "C" int sk_ce_blocks(int M);
 int sk_ce_launch(const bf16* logits, const int64_t* labels, bf16* dlogits, float* partial, float* row_nll,
                  float* stats_out, int M, int T, int V, int ldl, float num_items, float dloss, cudaStream_t s,
                  const float* row_weight = nullptr);
+int sk_ce_chunk_launch(const bf16* logits_chunk, const int64_t* labels, bf16* dlogits_chunk, float* partial, int row0, int rows,
+                       int M, int T, int V, int ldl, float grad_scale, cudaStream_t s);
+int sk_ce_finalize_launch(const float* partial, int M, float num_items, float* stats_out, cudaStream_t s);
 int sk_gradnorm_launch(const bf16* g, const long* chunk_start, const int* chunk_len, int n_chunks,
                        const int* tensor_chunk_begin, int n_tensors, float* partial, float max_norm, int emulate_bf16,
                        float* stats_out, cudaStream_t s);

@@ -26,10 +26,13 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const bf16* __
   }
 }
 
-// dE_f32[ids[m], :] += dx[m, :]   (fp32 atomics into a zeroed scratch; vocab is tiny so collisions are heavy but
-// the traffic is negligible next to the GEMMs)
+// dE_fix[ids[m], :] += dx[m, :] in 64-bit FIXED POINT (2^-40 units): integer addition is associative, so the atomics may
+// land in any order and the result is still bit-identical run to run (fp32 atomicAdd is not).  |sum| < 2^23 and terms
+// below 2^-41 vanish -- both far outside what a bf16 gradient row can hold.  Vocab is tiny for unit LMs (heavy
+// collisions, negligible traffic next to the GEMMs); for text+unit vocabularies the scratch is Vpad x D x 8 bytes.
+constexpr float EMBED_FIX_SCALE = 1099511627776.0f;          // 2^40
 __global__ void embed_bwd_scatter_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ dx,
-                                         float* __restrict__ scratch, int M, int D, int V) {
+                                         unsigned long long* __restrict__ scratch, int M, int D, int V) {
   const int vec_per_row = D / 8;
   const long total = (long)M * vec_per_row;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -39,22 +42,26 @@ __global__ void embed_bwd_scatter_kernel(const int64_t* __restrict__ ids, const 
     if (id < 0 || id >= V) continue;
     const uint4 v = ldg128_stream(dx + (size_t)m * D + c * 8);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    float* dst = scratch + (size_t)id * D + c * 8;
+    unsigned long long* dst = scratch + (size_t)id * D + c * 8;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 f = unpack_bf16(w[k]);
-      atomicAdd(dst + 2 * k, f.x);
-      atomicAdd(dst + 2 * k + 1, f.y);
+      if (f.x != 0.f) atomicAdd(dst + 2 * k, (unsigned long long)__float2ll_rn(f.x * EMBED_FIX_SCALE));
+      if (f.y != 0.f) atomicAdd(dst + 2 * k + 1, (unsigned long long)__float2ll_rn(f.y * EMBED_FIX_SCALE));
     }
   }
 }
 
-// grad[i] = bf16(float(grad[i]) * keep + scratch[i])
-__global__ void add_f32_into_bf16_kernel(bf16* __restrict__ grad, const float* __restrict__ scratch, long n, int keep) {
+// grad[i] = bf16(float(grad[i]) * keep + fix[i] * 2^-40)
+__global__ void add_fix_into_bf16_kernel(bf16* __restrict__ grad, const unsigned long long* __restrict__ scratch, long n, int keep) {
   for (long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 8; i < n; i += (long)gridDim.x * blockDim.x * 8) {
-    const float4 a = *reinterpret_cast<const float4*>(scratch + i);
-    const float4 b = *reinterpret_cast<const float4*>(scratch + i + 4);
-    float s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(scratch + i + k);
+      s[k] = (float)((double)(long long)a.x * (1.0 / 1099511627776.0));
+      s[k + 1] = (float)((double)(long long)a.y * (1.0 / 1099511627776.0));
+    }
     if (keep) {
       const uint4 g = *reinterpret_cast<const uint4*>(grad + i);
       const uint32_t w[4] = {g.x, g.y, g.z, g.w};
@@ -488,15 +495,17 @@ ce_fwd_bwd_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ l
 __global__ void __launch_bounds__(256)
 ce_large_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ labels, bf16* __restrict__ dlogits,
                 float* __restrict__ partial /*[M][2]*/, float* __restrict__ row_nll, const float* __restrict__ row_weight,
-                int M, int T, int V, int ldl, float grad_scale) {
+                int M, int T, int V, int ldl, float grad_scale, int row0) {
+  // row0 > 0: `logits` / `dlogits` hold a CHUNK of rows starting at global row row0 (chunked lm_head, lm_step.cu);
+  // labels, partial, row_nll and row_weight are always indexed by the global row
   __shared__ float s_m[8], s_s[8];
-  const int row = blockIdx.x;
+  const int row = row0 + blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = row % T;
   long target = -100;
   if (t < T - 1) target = labels[row + 1];
   const bool valid = (target >= 0 && target < V);
-  const bf16* lrow = logits + (size_t)row * ldl;
+  const bf16* lrow = logits + (size_t)blockIdx.x * ldl;
   const int nvec = ldl / 8;
   float m = -INFINITY, sum = 0.f;
   for (int c = threadIdx.x; c < nvec; c += 256) {
@@ -548,7 +557,7 @@ ce_large_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ lab
   if (dlogits) {
     const float gs = row_weight ? grad_scale * row_weight[row] : grad_scale;
     const float nlse2 = -lse * 1.4426950408889634f;
-    bf16* drow = dlogits + (size_t)row * ldl;
+    bf16* drow = dlogits + (size_t)blockIdx.x * ldl;
     for (int c = threadIdx.x; c < nvec; c += 256) {
       float o[8];
       if (valid) {
@@ -794,10 +803,11 @@ int sk_embed_fwd_launch(const int64_t* ids, const bf16* E, bf16* out, int M, int
 int sk_embed_bwd_launch(const int64_t* ids, const bf16* dx, float* scratch, bf16* dE, int M, int D, int V, int Vpad,
                         int accumulate, cudaStream_t s) {
   SK_REQUIRE(D % 8 == 0, "embed: D must be a multiple of 8");
-  SK_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)Vpad * D * sizeof(float), s));
-  embed_bwd_scatter_kernel<<<grid_for((long)M * D / 8, 256), 256, 0, s>>>(ids, dx, scratch, M, D, V);
+  unsigned long long* fix = reinterpret_cast<unsigned long long*>(scratch);   // Vpad * D 64-bit words
+  SK_CUDA_CHECK(cudaMemsetAsync(fix, 0, (size_t)Vpad * D * sizeof(unsigned long long), s));
+  embed_bwd_scatter_kernel<<<grid_for((long)M * D / 8, 256), 256, 0, s>>>(ids, dx, fix, M, D, V);
   SK_LAUNCH_CHECK();
-  add_f32_into_bf16_kernel<<<grid_for((long)Vpad * D / 8, 256), 256, 0, s>>>(dE, scratch, (long)Vpad * D, accumulate);
+  add_fix_into_bf16_kernel<<<grid_for((long)Vpad * D / 8, 256), 256, 0, s>>>(dE, fix, (long)Vpad * D, accumulate);
   SK_LAUNCH_CHECK();
   return 0;
 }
@@ -870,7 +880,7 @@ int sk_ce_launch(const bf16* logits, const int64_t* labels, bf16* dlogits, float
     ce_fwd_bwd_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(logits, labels, dlogits, partial, row_nll, row_weight, M, T, V, ldl, gs);
   } else {                                   // text + unit vocabularies: one block per row, two passes
     blocks = M;
-    ce_large_kernel<<<blocks, 256, 0, s>>>(logits, labels, dlogits, partial, row_nll, row_weight, M, T, V, ldl, gs);
+    ce_large_kernel<<<blocks, 256, 0, s>>>(logits, labels, dlogits, partial, row_nll, row_weight, M, T, V, ldl, gs, 0);
   }
   SK_LAUNCH_CHECK();
   ce_finalize_kernel<<<1, 256, 0, s>>>(partial, blocks, num_items, stats_out);
@@ -879,6 +889,21 @@ int sk_ce_launch(const bf16* logits, const int64_t* labels, bf16* dlogits, float
     scale_by_inv_count_kernel<<<grid_for((long)M * ldl / 8, 256), 256, 0, s>>>(dlogits, (long)M * ldl, stats_out);
     SK_LAUNCH_CHECK();
   }
+  return 0;
+}
+// Chunked form for large vocabularies: rows [row0, row0 + rows) of the batch, whose logits sit at `logits_chunk` (the
+// gradient is written in place when dlogits_chunk == logits_chunk: every element is read, then overwritten, by the same
+// thread).  partial holds one (nll, valid) pair per GLOBAL row; sk_ce_finalize_launch sums them once all chunks are done.
+int sk_ce_chunk_launch(const bf16* logits_chunk, const int64_t* labels, bf16* dlogits_chunk, float* partial, int row0, int rows,
+                       int M, int T, int V, int ldl, float grad_scale, cudaStream_t s) {
+  SK_REQUIRE(ldl % 8 == 0 && V <= ldl && rows > 0 && row0 >= 0 && row0 + rows <= M, "ce chunk: bad arguments");
+  ce_large_kernel<<<rows, 256, 0, s>>>(logits_chunk, labels, dlogits_chunk, partial, nullptr, nullptr, M, T, V, ldl, grad_scale, row0);
+  SK_LAUNCH_CHECK();
+  return 0;
+}
+int sk_ce_finalize_launch(const float* partial, int M, float num_items, float* stats_out, cudaStream_t s) {
+  ce_finalize_kernel<<<1, 256, 0, s>>>(partial, M, num_items, stats_out);
+  SK_LAUNCH_CHECK();
   return 0;
 }
 int sk_gradnorm_launch(const bf16* g, const long* chunk_start, const int* chunk_len, int n_chunks,

@@ -52,6 +52,7 @@ struct SkLm {
   float* d_chunk_partial = nullptr;
   int n_chunks = 0, n_norm_groups = 0;
   int last_B = 0, last_T = 0;
+  int head_chunk = 0;   // > 0: rows per chunk of the chunked lm_head + CE (large vocabularies), 0: one pass
   // optional: events recorded on the compute stream as soon as a layer's gradients are final (index = layer; index
   // n_layers = lm_head / final-norm part), so the host can start that bucket's all-reduce while backward continues
   std::vector<cudaEvent_t> bwd_events;
@@ -103,7 +104,9 @@ WsLayout make_layout(const SkLm* lm, int B, int T) {
   w.hf = take(w.sX);
   w.rstdf = take(w.srstd);
   w.logits = take(M * lm->Vp * 2);
-  w.dlogits = take(M * lm->Vp * 2);
+  // large vocabularies run the lm_head + CE in row chunks with the gradient written in place (head_chunked below): no
+  // second [M, Vp] buffer
+  w.dlogits = lm->head_chunk > 0 ? w.logits : take(M * lm->Vp * 2);
   w.dxA = take(w.sX);
   w.dxB = take(w.sX);
   w.dh = take(w.sX);
@@ -114,7 +117,7 @@ WsLayout make_layout(const SkLm* lm, int B, int T) {
   w.dw_partial = take((int64_t)sk_rmsnorm_bwd_blocks() * lm->d * 4);
   w.colsum_partial = take((int64_t)sk_colsum_splits() * lm->qkv_dim * 4);
   w.ce_partial = take((int64_t)sk_ce_blocks((int)M) * 2 * 4);
-  w.embed_scratch = take((int64_t)lm->Vp * lm->d * 4);
+  w.embed_scratch = take((int64_t)lm->Vp * lm->d * 8);   // 64-bit fixed-point accumulators of the embedding gradient
   w.attn_partial = take((int64_t)B * lm->H * T * 128 * 4);   // per-head fp32 dK|dV partials (tcgen05 backward)
   w.seg_start = take(M * 4);   // document bounds of packed batches (position_ids given), int32 per token
   w.seg_end = take(M * 4);
@@ -157,10 +160,11 @@ int linear_qkv_rope(const SkLm* lm, int M, int T, const bf16* x, const bf16* W, 
                                (lm->H + lm->KVH) * lm->hd, lm->cfg.max_positions, s);
 }
 
-int check_bound(const SkLm* lm, int B, int T, const WsLayout& w) {
+int check_bound(const SkLm* lm, int B, int T, const WsLayout& w, const int32_t* pos_ids) {
   SK_REQUIRE(lm->params && lm->ws, "sk_lm: sk_lm_bind has not been called");
-  SK_REQUIRE(B > 0 && T > 0 && T <= lm->cfg.max_positions, "sk_lm: bad batch shape B=%d T=%d (max_positions=%d)", B, T,
-             lm->cfg.max_positions);
+  // a packed row (position_ids given) may be longer than the RoPE tables: positions restart per document
+  SK_REQUIRE(B > 0 && T > 0 && (T <= lm->cfg.max_positions || pos_ids != nullptr),
+             "sk_lm: bad batch shape B=%d T=%d (max_positions=%d; longer rows need position_ids)", B, T, lm->cfg.max_positions);
   SK_REQUIRE(w.total <= lm->ws_bytes, "sk_lm: workspace too small: need %lld bytes, bound %lld", (long long)w.total,
              (long long)lm->ws_bytes);
   return 0;
@@ -168,7 +172,7 @@ int check_bound(const SkLm* lm, int B, int T, const WsLayout& w) {
 
 int forward_impl(SkLm* lm, const int64_t* ids, const int64_t* labels, const int32_t* pos_ids, int B, int T,
                  float num_items, float dloss, bool want_dlogits, float* stats, const WsLayout& w, cudaStream_t s,
-                 float* row_nll = nullptr) {
+                 float* row_nll = nullptr, bool with_head = true) {
   const int M = B * T, d = lm->d, F = lm->F, L = lm->L;
   const bf16* P = lm->params;
   bf16* X0 = wsp<bf16>(lm, w.X);
@@ -207,19 +211,49 @@ int forward_impl(SkLm* lm, const int64_t* ids, const int64_t* labels, const int3
   bf16* xL = wsp<bf16>(lm, w.X + w.sX * L);
   bf16* hf = wsp<bf16>(lm, w.hf);
   SK_TRY(sk_rmsnorm_fwd_launch(xL, P + lm->off_final_norm, hf, wsp<float>(lm, w.rstdf), M, d, lm->cfg.rms_eps, s));
+  lm->last_B = B;
+  lm->last_T = T;
+  if (!with_head) return 0;
   bf16* logits = wsp<bf16>(lm, w.logits);
   SK_TRY(linear_fwd(M, lm->Vp, d, hf, P + lm->off_head, logits, nullptr, nullptr, s));
   if (labels) {
     SK_TRY(sk_ce_launch(logits, labels, want_dlogits ? wsp<bf16>(lm, w.dlogits) : nullptr, wsp<float>(lm, w.ce_partial),
                         row_nll, stats, M, T, lm->V, lm->Vp, num_items, dloss, s));
   }
-  lm->last_B = B;
-  lm->last_T = T;
   return 0;
 }
 
+// lm_head + compute_loss + their backward for text+unit vocabularies (~152 k columns; BASELINE cfg-4), in row chunks:
+//   logits_c = hf_c * E^T  ->  CE on the chunk, gradient written over the logits  ->  dh_c = dlogits_c * E,  dE += dlogits_c^T hf_c
+// Only [chunk, Vp] logits ever exist (0.6 GB at 2048 rows instead of 2 x 2.5 GB at [8192, 152 k]) and every element
+// moves through HBM as in the one-pass form; the price is one read-modify-write of dE per extra chunk.  (A fully fused
+// "flash" CE would recompute the logits GEMM in the backward pass -- 2.2 TFLOP at this shape, more time than the 7.5 GB
+// of logits traffic it removes: DESIGN.md §4.)  The sums per row meet in `ce_partial`, finalised once.
+int head_chunked(SkLm* lm, const int64_t* labels, int B, int T, float num_items, float dloss, int accumulate, float* stats,
+                 const WsLayout& w, cudaStream_t s) {
+  const int M = B * T, d = lm->d;
+  SK_REQUIRE(num_items > 0.f, "sk_lm: training with a large vocabulary needs num_items_in_batch (the 'sum / num_items' loss of "
+                              "slamkit/model/unit_lm.py:26-28): the gradient scale must be known before the first chunk");
+  const bf16* P = lm->params;
+  bf16* G = lm->grads;
+  bf16* hf = wsp<bf16>(lm, w.hf);
+  bf16* dh = wsp<bf16>(lm, w.dh);
+  bf16* chunk = wsp<bf16>(lm, w.logits);
+  float* partial = wsp<float>(lm, w.ce_partial);
+  const float gs = dloss / num_items;
+  for (int r0 = 0; r0 < M; r0 += lm->head_chunk) {
+    const int rows = std::min(lm->head_chunk, M - r0);
+    SK_TRY(linear_fwd(rows, lm->Vp, d, hf + (size_t)r0 * d, P + lm->off_head, chunk, nullptr, nullptr, s));
+    SK_TRY(sk_ce_chunk_launch(chunk, labels, chunk, partial, r0, rows, M, T, lm->V, lm->Vp, gs, s));
+    SK_TRY(linear_dgrad(rows, lm->Vp, d, chunk, P + lm->off_head, dh + (size_t)r0 * d, s));
+    SK_TRY(linear_wgrad(rows, lm->Vp, d, chunk, hf + (size_t)r0 * d, G + lm->off_head, (accumulate || r0 > 0) ? 1 : 0, s,
+                        lm->ws + w.splitk, (size_t)w.splitk_bytes));
+  }
+  return sk_ce_finalize_launch(partial, M, num_items, stats, s);
+}
+
 int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, int T, int accumulate,
-                  const WsLayout& w, cudaStream_t s) {
+                  const WsLayout& w, cudaStream_t s, bool with_head = true) {
   const int M = B * T, d = lm->d, F = lm->F, L = lm->L, Q = lm->qkv_dim;
   const bf16* P = lm->params;
   bf16* G = lm->grads;
@@ -234,9 +268,11 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
   bf16* hf = wsp<bf16>(lm, w.hf);
   const float scale = 1.0f / sqrtf((float)lm->hd);
 
-  // lm_head
-  SK_TRY(linear_dgrad(M, lm->Vp, d, dlogits, P + lm->off_head, dh, s));
-  SK_TRY(linear_wgrad(M, lm->Vp, d, dlogits, hf, G + lm->off_head, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
+  // lm_head (already done chunk by chunk for large vocabularies)
+  if (with_head) {
+    SK_TRY(linear_dgrad(M, lm->Vp, d, dlogits, P + lm->off_head, dh, s));
+    SK_TRY(linear_wgrad(M, lm->Vp, d, dlogits, hf, G + lm->off_head, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
+  }
   SK_TRY(sk_rmsnorm_bwd_launch(dh, wsp<bf16>(lm, w.X + w.sX * L), P + lm->off_final_norm, wsp<float>(lm, w.rstdf),
                                nullptr, dxA, G + lm->off_final_norm, dwp, M, d, accumulate, s));
   if (!lm->bwd_events.empty()) SK_CUDA_CHECK(cudaEventRecord(lm->bwd_events[L], s));
@@ -303,6 +339,9 @@ int sk_lm_create(const SkLmConfig* cfg, SkLm** out) {
   lm->V = cfg->vocab_size;
   lm->Vp = (cfg->vocab_size + 63) / 64 * 64;
   lm->qkv_dim = (lm->H + 2 * lm->KVH) * lm->hd;
+  // text+unit vocabularies: chunked lm_head + CE (SK_HEAD_CHUNK=rows overrides, 0 turns it off)
+  lm->head_chunk = lm->Vp > 8192 ? 2048 : 0;
+  if (const char* e = getenv("SK_HEAD_CHUNK")) lm->head_chunk = (atoi(e) / 128) * 128;
   lm->lo.resize(lm->L);
   for (int l = 0; l < lm->L; ++l) {
     const std::string p = "layers." + std::to_string(l) + ".";
@@ -428,7 +467,7 @@ int sk_lm_forward(SkLm* lm, const int64_t* ids, const int64_t* labels, const int
   SK_REQUIRE(lm && ids, "sk_lm_forward: null argument");
   SK_REQUIRE(labels == nullptr || stats != nullptr, "sk_lm_forward: stats is required when labels are given");
   const WsLayout w = make_layout(lm, B, T);
-  SK_TRY(check_bound(lm, B, T, w));
+  SK_TRY(check_bound(lm, B, T, w, pos_ids));
   return forward_impl(lm, ids, labels, pos_ids, B, T, num_items, 1.0f, false, stats, w, (cudaStream_t)stream);
 }
 
@@ -437,7 +476,12 @@ int sk_lm_forward_backward(SkLm* lm, const int64_t* ids, const int64_t* labels, 
   SK_REQUIRE(lm && ids && labels && stats, "sk_lm_forward_backward: null argument");
   SK_REQUIRE(lm->grads, "sk_lm_forward_backward: no gradient buffer bound");
   const WsLayout w = make_layout(lm, B, T);
-  SK_TRY(check_bound(lm, B, T, w));
+  SK_TRY(check_bound(lm, B, T, w, pos_ids));
+  if (lm->head_chunk > 0) {
+    SK_TRY(forward_impl(lm, ids, labels, pos_ids, B, T, num_items, dloss, true, stats, w, (cudaStream_t)stream, nullptr, false));
+    SK_TRY(head_chunked(lm, labels, B, T, num_items, dloss, accumulate, stats, w, (cudaStream_t)stream));
+    return backward_impl(lm, ids, pos_ids, B, T, accumulate, w, (cudaStream_t)stream, false);
+  }
   SK_TRY(forward_impl(lm, ids, labels, pos_ids, B, T, num_items, dloss, true, stats, w, (cudaStream_t)stream));
   return backward_impl(lm, ids, pos_ids, B, T, accumulate, w, (cudaStream_t)stream);
 }
@@ -458,7 +502,7 @@ int sk_lm_forward_rows(SkLm* lm, const int64_t* ids, const int64_t* labels, cons
                        float* row_nll, float* stats, void* stream) {
   SK_REQUIRE(lm && ids && labels && row_nll && stats, "sk_lm_forward_rows: null argument");
   const WsLayout w = make_layout(lm, B, T);
-  SK_TRY(check_bound(lm, B, T, w));
+  SK_TRY(check_bound(lm, B, T, w, pos_ids));
   return forward_impl(lm, ids, labels, pos_ids, B, T, 1.0f, 1.0f, false, stats, w, (cudaStream_t)stream, row_nll);
 }
 
@@ -468,7 +512,7 @@ int sk_lm_backward_weighted(SkLm* lm, const int64_t* ids, const int64_t* labels,
   SK_REQUIRE(lm->grads, "sk_lm_backward_weighted: no gradient buffer bound");
   SK_REQUIRE(lm->last_B == B && lm->last_T == T, "sk_lm_backward_weighted: call sk_lm_forward_rows on the same batch first");
   const WsLayout w = make_layout(lm, B, T);
-  SK_TRY(check_bound(lm, B, T, w));
+  SK_TRY(check_bound(lm, B, T, w, pos_ids));
   cudaStream_t s = (cudaStream_t)stream;
   // d loss / d logits[row] = row_weight[row] * (softmax - onehot): recomputed from the logits the forward pass left in
   // the workspace (num_items = 1, dloss = 1: the caller's weights carry every scale factor)

@@ -54,10 +54,18 @@ def collate_pairs(rows: Sequence[Dict[str, List[int]]], pad_id: int = 0):
 
 
 class B200DPOTrainer:
+    """One optimiser step = `gradient_accumulation_steps` micro-batches of concatenated [chosen ; rejected] rows.  Under
+    torchrun every rank holds its own micro-batches; trl runs DDP, i.e. the MEAN over ranks of each rank's mean loss, so
+    the per-sequence weights carry 1 / (pairs_per_micro_batch * grad_accum * world) and the flat gradient buffer is
+    SUM-all-reduced (`trainer.GradSync`, overlapped with the backward pass) before the clip + AdamW step."""
+
     def __init__(self, policy: B200UnitLM, reference: B200UnitLM, beta: float = 0.1, lr: float = 5e-5,
-                 max_grad_norm: float = 0.5, weight_decay: float = 0.0):
+                 max_grad_norm: float = 0.5, weight_decay: float = 0.0, grad_accum: int = 1, overlap_comm: bool = True):
+        from .trainer import GradSync
         self.policy, self.reference, self.beta = policy, reference, beta
         self.opt = B200AdamW(policy, lr=lr, max_grad_norm=max_grad_norm, weight_decay=weight_decay)
+        self.sync = GradSync(policy, overlap=overlap_comm)
+        self.grad_accum = grad_accum
 
     @staticmethod
     def _seq_logps(model: B200UnitLM, ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
@@ -68,8 +76,9 @@ class B200DPOTrainer:
                                              L.ptr(model.stats), L.stream_ptr()))
         return -row_nll.view(B, T).sum(dim=1)
 
-    def step(self, ids: torch.Tensor, labels: torch.Tensor, lr: Optional[float] = None) -> Dict[str, torch.Tensor]:
-        """ids/labels: the concatenated [2N, T] batch of `collate_pairs`. One optimiser step; returns device scalars."""
+    def micro_step(self, ids: torch.Tensor, labels: torch.Tensor, accumulate: bool) -> Dict[str, torch.Tensor]:
+        """Forward of reference + policy and the weighted backward of one concatenated [2N, T] batch of `collate_pairs`;
+        gradients are written (accumulate=False) or added (True) to the policy's flat gradient buffer."""
         pol, ref = self.policy, self.reference
         ids, labels = ids.to(pol.device).contiguous(), labels.to(pol.device).contiguous()
         n = ids.shape[0] // 2
@@ -80,11 +89,25 @@ class B200DPOTrainer:
         loss = -torch.nn.functional.logsigmoid(z).mean()
         # d loss / d pi_c = -beta*sigmoid(-z)/n ; d loss / d pi_r = +beta*sigmoid(-z)/n ; pi = -sum nll, and the kernel
         # applies w * (softmax - onehot) = w * d nll / d logits  ->  w_c = +beta*sigmoid(-z)/n, w_r = -beta*sigmoid(-z)/n
-        g = self.beta * torch.sigmoid(-z) / n
+        g = self.beta * torch.sigmoid(-z) / (n * self.grad_accum * self.sync.world)
         w_seq = torch.cat([g, -g])
         row_w = w_seq[:, None].expand(B, T).contiguous().view(-1).float()
-        L.check(pol.lib.sk_lm_backward_weighted(pol._h, L.ptr(ids), L.ptr(labels), None, B, T, L.ptr(row_w), 0,
+        L.check(pol.lib.sk_lm_backward_weighted(pol._h, L.ptr(ids), L.ptr(labels), None, B, T, L.ptr(row_w), int(accumulate),
                                                 L.ptr(pol.stats), L.stream_ptr()))
-        self.opt.step(lr=lr)
         return {"loss": loss, "rewards_chosen": self.beta * (pol_lp[:n] - ref_lp[:n]),
                 "rewards_rejected": self.beta * (pol_lp[n:] - ref_lp[n:]), "logits_z": z}
+
+    def step(self, ids, labels, lr: Optional[float] = None) -> Dict[str, torch.Tensor]:
+        """One optimiser step.  ids / labels: one concatenated batch (grad_accum == 1) or lists of `grad_accum` batches.
+        Returns device tensors of the LAST micro-batch plus `loss` = mean over the accumulation window (this rank)."""
+        if torch.is_tensor(ids):
+            ids, labels = [ids], [labels]
+        assert len(ids) == self.grad_accum == len(labels), "one [2N, T] batch per accumulation step"
+        out, loss = None, 0.0
+        for i, (a, b) in enumerate(zip(ids, labels)):
+            out = self.micro_step(a, b, accumulate=i > 0)
+            loss = loss + out["loss"] / self.grad_accum
+        self.sync.reduce()
+        self.opt.step(lr=lr)
+        out["loss"] = loss
+        return out

@@ -38,20 +38,21 @@ def hubert_b200_from_cfg(pretrained_model: str = "facebook/hubert-base-ls960",
     return HubertB200FeatureExtractor(cfg, params, device=device, max_batch=max_batch, max_samples=max_samples)
 
 
-def tlm_b200_from_cfg(cfg, device: str = "cuda:0", max_batch: int = 8):
+def tlm_b200_from_cfg(cfg, device: str = "cuda:0", max_batch: int = 8, max_seq: Optional[int] = None):
     """`cfg` is the reference's model config node (config/model/*.yaml): context_len, config_args{base_model_name,
-    vocab_size, twist_init, rope_theta, ...}."""
+    vocab_size, twist_init, rope_theta, ...}.  Raises OSError when the base model cannot be reached (offline box) and
+    ValueError when its architecture has no B200 kernels (anything but Qwen2)."""
     from transformers import AutoConfig
     from .lm import B200UnitLM, LMConfig
 
     args = cfg["config_args"] if isinstance(cfg, dict) else cfg.config_args
     get = args.get if hasattr(args, "get") else (lambda k, d=None: getattr(args, k, d))
     base = AutoConfig.from_pretrained(get("base_model_name"))
-    lm_cfg = LMConfig.from_hf(base, vocab_size=get("vocab_size", 502))
+    ctx = int(cfg["context_len"] if isinstance(cfg, dict) else cfg.context_len)
+    lm_cfg = LMConfig.from_hf(base, vocab_size=get("vocab_size", 502), max_positions=max(2048, ctx))
     if get("rope_theta") is not None:
         lm_cfg.rope_theta = float(get("rope_theta"))
-    ctx = (cfg["context_len"] if isinstance(cfg, dict) else cfg.context_len)
-    model = B200UnitLM(lm_cfg, device=device, max_batch=max_batch, max_seq=int(ctx))
+    model = B200UnitLM(lm_cfg, device=device, max_batch=max_batch, max_seq=int(max_seq or ctx))
     if get("twist_init", True):
         from transformers import AutoModelForCausalLM
         import torch

@@ -37,6 +37,15 @@ class LMConfig:
 
     @staticmethod
     def from_hf(cfg, vocab_size: Optional[int] = None, max_positions: int = 2048) -> "LMConfig":
+        """From an HF config of the base model.  Only the Qwen2 decoder architecture (RMSNorm, rotary GQA attention with
+        q/k/v bias, SwiGLU, no o/MLP bias) has sm_100a kernels behind it: anything else (e.g. the OPT-125M of
+        config/model/twist.yaml) is refused instead of being silently trained as a different model."""
+        mt = getattr(cfg, "model_type", None)
+        if mt != "qwen2":
+            raise ValueError(f"unsupported base architecture '{mt}': the B200 train path implements the Qwen2 decoder "
+                             "(use model=slam, config/model/slam.yaml)")
+        if getattr(cfg, "head_dim", None) not in (None, 64) or cfg.hidden_size // cfg.num_attention_heads != 64:
+            raise ValueError("unsupported attention geometry: the sm_100a attention kernels need head_dim 64")
         rp = getattr(cfg, "rope_parameters", None) or {}
         theta = rp.get("rope_theta", getattr(cfg, "rope_theta", 10000.0))
         return LMConfig(
@@ -44,7 +53,8 @@ class LMConfig:
             n_heads=cfg.num_attention_heads, n_kv_heads=cfg.num_key_value_heads,
             head_dim=getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads,
             ffn=cfg.intermediate_size, max_positions=max_positions, rms_eps=cfg.rms_norm_eps, rope_theta=float(theta),
-            tie_embeddings=bool(cfg.tie_word_embeddings), qkv_bias=True, pad_token_id=cfg.pad_token_id or 0)
+            tie_embeddings=bool(cfg.tie_word_embeddings), qkv_bias=bool(getattr(cfg, "attention_bias", True)),
+            pad_token_id=cfg.pad_token_id or 0)
 
 
 def rope_tables(theta: float, head_dim: int, max_positions: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -61,6 +71,50 @@ class LMOutput:
     loss: Optional[torch.Tensor]
     logits: Optional[torch.Tensor]
     stats: Optional[torch.Tensor] = None   # device fp32[3]: loss, n_valid_targets, nll_sum
+
+
+def write_unit_lm_checkpoint(save_directory: str, state_dict_hf: Dict[str, torch.Tensor], config: "LMConfig",
+                             base_model_name: str = "Qwen/Qwen2.5-0.5B") -> None:
+    """Writes `model.safetensors` with the `lm.`-prefixed names of `UnitLM.state_dict()` (base_model_prefix = "lm",
+    slamkit/model/unit_lm.py:87) and a `config.json` in the `UnitLMConfig` layout (unit_lm.py:32-79), so that the
+    reference's `UnitLM.from_pretrained(dir)` / cli/eval.py consume a B200-trained model.  Pure host code (no CUDA):
+    tests/test_host_cpu.py loads such a directory with the reference's own class."""
+    import json
+    import os
+    from safetensors.torch import save_file
+    os.makedirs(save_directory, exist_ok=True)
+    c = config
+    sd = {k: v.detach().contiguous().cpu() for k, v in state_dict_hf.items()
+          if k != "lm.lm_head.weight" or not c.tie_embeddings}
+    save_file(sd, os.path.join(save_directory, "model.safetensors"), metadata={"format": "pt"})
+    base = {"model_type": "qwen2", "architectures": ["Qwen2ForCausalLM"], "hidden_size": c.hidden,
+            "intermediate_size": c.ffn, "num_hidden_layers": c.n_layers, "num_attention_heads": c.n_heads,
+            "num_key_value_heads": c.n_kv_heads, "vocab_size": c.vocab_size, "rms_norm_eps": c.rms_eps,
+            "max_position_embeddings": c.max_positions, "tie_word_embeddings": c.tie_embeddings, "hidden_act": "silu",
+            "rope_parameters": {"rope_theta": c.rope_theta, "rope_type": "default"}, "rope_theta": c.rope_theta,
+            "pad_token_id": c.pad_token_id, "bos_token_id": 1, "eos_token_id": 1, "torch_dtype": "bfloat16"}
+    cfg = {"model_type": "speech_language_model", "architectures": ["UnitLM"], "base_model_name": base_model_name,
+           "base_config": base, "vocab_size": c.vocab_size, "twist_init": False, "use_cache": False,
+           "tie_word_embeddings": c.tie_embeddings, "torch_dtype": "bfloat16",
+           "max_position_embeddings": c.max_positions}
+    with open(os.path.join(save_directory, "config.json"), "w") as f:
+        json.dump(cfg, f, indent=2)
+
+
+def check_right_padded(attention_mask: Optional[torch.Tensor]) -> None:
+    """The kernels apply the causal mask only (plus document boundaries from position_ids).  That is exact for the
+    reference's batches -- right-padded by DataCollatorForLanguageModeling / `padding_side = "right"`
+    (slamkit/data/hf_dataset.py:61-64, unit_tokeniser.py:45) -- because a non-pad query never looks at a later pad key.
+    Any other mask (left padding, holes) would silently change the result, so it is refused."""
+    if attention_mask is None:
+        return
+    m = attention_mask
+    if m.dim() != 2:
+        raise ValueError("attention_mask must be [batch, seq] (explicit 4-D masks are not supported on the B200 path)")
+    ok = bool(((m[:, 1:] != 0) <= (m[:, :-1] != 0)).all()) if m.shape[1] > 1 else True
+    if not ok:
+        raise ValueError("attention_mask is not right-padding (ones then zeros per row): the B200 attention kernels "
+                         "implement causal masking only")
 
 
 class B200UnitLM:
@@ -206,27 +260,7 @@ class B200UnitLM:
 
     # ---- checkpoints (HF layout) ------------------------------------------------------------
     def save_pretrained(self, save_directory: str, base_model_name: str = "Qwen/Qwen2.5-0.5B") -> None:
-        """Writes `model.safetensors` with the `lm.`-prefixed names of `UnitLM.state_dict()` (base_model_prefix = "lm",
-        slamkit/model/unit_lm.py:87) and a `config.json` in the `UnitLMConfig` layout (unit_lm.py:32-79), so that
-        `UnitLM.from_pretrained(dir)` / cli/eval.py of the reference can consume a B200-trained model."""
-        import json
-        import os
-        from safetensors.torch import save_file
-        os.makedirs(save_directory, exist_ok=True)
-        sd = {k: v.contiguous().cpu() for k, v in self.state_dict_hf().items() if k != "lm.lm_head.weight" or not self.config.tie_embeddings}
-        save_file(sd, os.path.join(save_directory, "model.safetensors"), metadata={"format": "pt"})
-        c = self.config
-        base = {"model_type": "qwen2", "architectures": ["Qwen2ForCausalLM"], "hidden_size": c.hidden,
-                "intermediate_size": c.ffn, "num_hidden_layers": c.n_layers, "num_attention_heads": c.n_heads,
-                "num_key_value_heads": c.n_kv_heads, "vocab_size": c.vocab_size, "rms_norm_eps": c.rms_eps,
-                "max_position_embeddings": c.max_positions, "tie_word_embeddings": c.tie_embeddings, "hidden_act": "silu",
-                "rope_parameters": {"rope_theta": c.rope_theta, "rope_type": "default"}, "rope_theta": c.rope_theta,
-                "pad_token_id": c.pad_token_id, "bos_token_id": 1, "eos_token_id": 1, "torch_dtype": "bfloat16"}
-        cfg = {"model_type": "speech_language_model", "architectures": ["UnitLM"], "base_model_name": base_model_name,
-               "base_config": base, "vocab_size": c.vocab_size, "twist_init": False, "use_cache": False,
-               "tie_word_embeddings": c.tie_embeddings, "torch_dtype": "bfloat16",
-               "max_position_embeddings": c.max_positions}
-        json.dump(cfg, open(os.path.join(save_directory, "config.json"), "w"), indent=2)
+        write_unit_lm_checkpoint(save_directory, self.state_dict_hf(), self.config, base_model_name)
 
     @classmethod
     def from_pretrained(cls, directory: str, device: str = "cuda:0", max_batch: int = 8, max_seq: int = 1024,
@@ -271,6 +305,7 @@ class B200UnitLM:
                 num_items_in_batch: Optional[float] = None, **_) -> LMOutput:
         """Forward only (eval / scoring). Padding is right-padding as produced by the reference collators
         (slamkit/data/hf_dataset.py:61-64), so the causal mask alone is exact for the non-pad positions."""
+        check_right_padded(attention_mask)
         B, T, ids, pos = self._prep(input_ids, position_ids)
         lab = labels.to(self.device).contiguous() if labels is not None else None
         ni = float(num_items_in_batch) if num_items_in_batch is not None else 0.0

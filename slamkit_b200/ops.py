@@ -83,7 +83,7 @@ def embed_fwd(ids: torch.Tensor, table: torch.Tensor, vocab: int) -> torch.Tenso
 def embed_bwd(ids: torch.Tensor, dx: torch.Tensor, dtable: torch.Tensor, vocab: int, accumulate: bool) -> None:
     lib = L.require_cuda()
     M, D = dx.shape
-    scratch = torch.empty((dtable.shape[0], D), device=dx.device, dtype=torch.float32)
+    scratch = torch.empty((dtable.shape[0], D), device=dx.device, dtype=torch.int64)   # 64-bit fixed-point accumulators
     L.check(lib.sk_embed_bwd(L.ptr(ids), L.ptr(dx), L.ptr(scratch), L.ptr(dtable), M, D, vocab, dtable.shape[0],
                              int(accumulate), L.stream_ptr()))
 

@@ -101,3 +101,53 @@ class B200UnitTokeniser:
 
     def get_ignore_tokens(self, _=None):
         return None
+
+
+SPEECH_TOKEN, TEXT_TOKEN = "<speech>", "<text>"
+
+
+class B200InterleavingTokeniser:
+    """Host-side mirror of `slamkit.tokeniser.interleaving_tokeniser.InterleavingTokeniser` for the TRAINING input
+    contract of the interleaved speech-text recipe (config/tokeniser/interleaved_hubert_25.yaml, BASELINE cfg-4): an HF
+    text tokenizer extended with `<Un0>..<Un{n-1}>`, `<speech>`, `<text>` (interleaving_tokeniser.py:121-127), so the
+    model vocabulary is text + units (~152 k rows for Qwen2.5).  `prepare_sample` / `string_tokenise` / `len` are what
+    cli/train.py needs; `audio_represent` goes through the same B200 feature extractor as the unit tokeniser.  Building
+    the interleaved strings from word alignments (`stringify_representation(mode='train')`) is text-side preprocessing
+    outside the hot path and is not re-implemented: prepare such token files with the reference."""
+
+    def __init__(self, speech_tokeniser=None, dedup: bool = True, pad_token_id: int = 0, num_units: int = 500,
+                 load_fe: bool = True, text_tokeniser_path: str = "facebook/opt-125m", interleave_method: str = "random",
+                 interleave_span: Optional[int] = None, interleave_prob: Optional[float] = None):
+        from transformers import AutoTokenizer
+        self.model = speech_tokeniser if load_fe else None
+        self.dedup, self.pad_token_id, self.num_units = dedup, pad_token_id, num_units
+        tk = AutoTokenizer.from_pretrained(text_tokeniser_path)
+        tk.pad_token_id = pad_token_id
+        tk.padding_side = "right"
+        tk.add_tokens([f"<Un{x}>" for x in range(num_units)] + [SPEECH_TOKEN, TEXT_TOKEN])
+        self.text_tokeniser = tk
+        self.interleave_method, self.interleave_span, self.interleave_prob = interleave_method, interleave_span, interleave_prob
+
+    def __len__(self) -> int:
+        return len(self.text_tokeniser)
+
+    def audio_represent(self, wav: torch.Tensor, lens: Optional[torch.Tensor] = None) -> List[Dict]:
+        return B200UnitTokeniser.audio_represent(self, wav, lens)
+
+    def stringify_representation(self, reps: List[Dict], mode: str = "test") -> List[str]:
+        if mode == "train":
+            raise NotImplementedError("interleaving from word alignments is text-side preprocessing outside the B200 hot "
+                                      "path; prepare interleaved token files with the reference's cli/prepare_tokens.py")
+        return ["".join(f"<Un{u}>" for u in cur["units"]) for cur in reps]
+
+    def string_tokenise(self, audio_repr, **kw) -> Dict:
+        return self.text_tokeniser(audio_repr, add_special_tokens=True, **kw)
+
+    def prepare_sample(self, sample: dict, **kw) -> Dict:
+        return self.string_tokenise(sample["audio_repr"], **kw)
+
+    def save_pretrained(self, save_directory: str, **_):
+        with open(f"{save_directory}/tokeniser_config.json", "w") as f:
+            json.dump({"dedup": self.dedup, "pad_token_id": self.pad_token_id, "num_units": self.num_units, "load_fe": False,
+                       "text_tokeniser_path": self.text_tokeniser.name_or_path, "interleave_method": self.interleave_method,
+                       "interleave_span": self.interleave_span, "interleave_prob": self.interleave_prob}, f)

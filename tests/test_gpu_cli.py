@@ -40,8 +40,9 @@ def test_extract_prepare_train_pipeline(tmp_path):
                       "training_args.per_device_train_batch_size=2", "+training_args.max_steps=12",
                       "+training_args.logging_steps=1", "training_args.warmup_steps=2", "training_args.warmup_ratio=0",
                       f"training_args.output_dir={tmp_path}/run"])
-    assert len(log) == 12 and log[-1]["loss"] < log[0]["loss"]
+    losses = [r["loss"] for r in log if "loss" in r]
+    assert len(losses) == 12 and losses[-1] < losses[0]
     assert os.path.exists(tmp_path / "run" / "model.safetensors") and os.path.exists(tmp_path / "run" / "config.json")
     st = json.load(open(tmp_path / "run" / "trainer_state.json"))
-    assert st["steps"] == 12 and st["eval_loss"] > 0
+    assert st["global_step"] == 12 and st["eval_loss"] > 0 and st["num_input_tokens_seen"] > 0
     assert json.load(open(tmp_path / "run" / "tokeniser_config.json"))["num_units"] == 500

@@ -221,10 +221,14 @@ def test_lm_packed_matches_reference_golden(golden_dir):
     assert rel_err(out.logits[0].float().cpu(), u16_to_bf16(z["logits_u16"])[0].float()) < 8e-3
 
 
-def test_lm_large_vocabulary_vs_oracle():
+@pytest.mark.parametrize("head_chunk", [0, 128])
+def test_lm_large_vocabulary_vs_oracle(head_chunk, monkeypatch):
     """A vocabulary far above the unit-only 502 (the interleaved text+unit configuration): lm_head GEMMs with thousands
-    of columns, the block-per-row CE kernel, a larger tied embedding in the optimiser."""
+    of columns, the block-per-row CE kernel, a larger tied embedding in the optimiser.  head_chunk = 128 forces the
+    chunked lm_head + CE that 152 k-column vocabularies use by default (logits exist one 128-row chunk at a time, the
+    gradient is written over them, dE accumulates over the chunks): 192 rows = one full and one ragged chunk."""
     from oracle import lm_oracle as O
+    monkeypatch.setenv("SK_HEAD_CHUNK", str(head_chunk))
     cfg_o = O.OracleLMConfig(vocab_size=4099, hidden=128, n_layers=2, n_heads=2, n_kv_heads=1, head_dim=64, ffn=256)
     m, p = _mk(cfg_o, 7, 2, 96)
     g = torch.Generator().manual_seed(1)
