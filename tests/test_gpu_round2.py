@@ -291,12 +291,16 @@ def _dp_worker(rank, world, port, out_dir):
     res = {}
     for overlap in (False, True):
         m, _ = _mk_lm(cfg_o, 11, 2 * world, 96, device=dev)
-        tr = B200Trainer(m, lr=0.0, warmup_steps=0, total_steps=4, overlap_comm=overlap)       # lr 0: weights stay put
+        tr = B200Trainer(m, lr=1e-12, min_lr=0.0, warmup_steps=0, total_steps=4, overlap_comm=overlap)   # lr ~0: weights stay put
         assert tr.sync.world == world and tr.sync.overlap == overlap
         # (1) the reduced flat gradient == the sum of the all-gathered per-rank gradients, bit for bit
         n_glob = float((labels != -100).sum())
         m.forward_backward(full[mine], labels[mine], num_items_in_batch=n_glob)
-        local = m.grads.clone()
+        local = m.grads.clone()                     # this rank's gradients, before any reduction
+        torch.cuda.synchronize()
+        # the step is deterministic: the same call again, now with the reduction riding on its backward pass (in overlap
+        # mode buckets are reduced IN PLACE while backward still runs, so `local` had to be taken from a separate pass)
+        m.forward_backward(full[mine], labels[mine], num_items_in_batch=n_glob)
         tr.sync.reduce()
         torch.cuda.synchronize()
         gathered = [torch.empty_like(local) for _ in range(world)]
@@ -306,7 +310,9 @@ def _dp_worker(rank, world, port, out_dir):
             want = (want + x.float())
         # NCCL sums bf16 pairwise in the same order for 2 ranks; for more ranks compare within bf16 rounding of the sum
         if world == 2:
-            assert torch.equal(m.grads, want.to(torch.bfloat16)), float((m.grads.float() - want).abs().max())
+            bad = (m.grads != want.to(torch.bfloat16)).nonzero().flatten()
+            assert bad.numel() == 0, (f"overlap={overlap}: {bad.numel()} of {m.grads.numel()} elements differ, first {int(bad[0])}, last {int(bad[-1])}; "
+                                      f"buckets {tr.sync.buckets} tail {tr.sync.tail}; max abs diff {float((m.grads.float() - want).abs().max())}")
         else:
             assert rel_err(m.grads.float().cpu(), want.cpu()) < 4e-3
         # (2) N-rank loss == 1-rank loss on the concatenated batch (HF average_tokens_across_devices semantics)
