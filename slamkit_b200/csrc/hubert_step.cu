@@ -28,7 +28,7 @@ struct LayerOff {
   int64_t wqkv, bqkv, wo, bo, ln1g, ln1b, w1, b1, w2, b2, ln2g, ln2b;
 };
 struct WsLayout {
-  int64_t stats, affine, act0, act1, lnc, x, xp, pc, h0, h1, qkv, ao, t1, ff, dot, n_frames, total;
+  int64_t stats, affine, conv0_b, act0, act1, lnc, x, xp, pc, h0, h1, qkv, ao, t1, ff, dot, n_frames, total;
 };
 int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 }  // namespace
@@ -81,6 +81,7 @@ WsLayout make_layout(const SkHubert* h, int B, int S) {
   auto hilo = [&](int64_t elems) { return take(2 * align_up(elems * 2, 256)); };  // hi then lo
   w.stats = take((int64_t)B * sk_conv0_nstat() * 8);
   w.affine = take((int64_t)B * h->C * 8);
+  w.conv0_b = take((int64_t)B * h->C * 64 * 2);   // per-clip B operand of the tensor-core conv0 (hubert_kernels.cu)
   w.act0 = hilo((int64_t)B * T[0] * h->C);
   w.act1 = hilo((int64_t)B * (h->nconv > 1 ? T[1] : 1) * h->C);
   w.lnc = hilo(M * h->C);
@@ -154,7 +155,7 @@ int forward_impl(SkHubert* h, const float* wav, const int64_t* lens, int B, int 
   SK_TRY(sk_conv0_launch(wav, h->w32 + h->conv0_w, h->w32 + h->gn_g, h->w32 + h->gn_b,
                          reinterpret_cast<double*>(h->ws + w.stats), reinterpret_cast<float2*>(h->ws + w.affine),
                          act[0].hi, act[0].lo, B, S, h->cfg.pad, T[0], C, h->cfg.conv_kernel[0], h->cfg.conv_stride[0],
-                         1e-5f, s));
+                         1e-5f, s, reinterpret_cast<bf16*>(h->ws + w.conv0_b)));
   if (dbg_stage == 100) return sk_hilo_to_f32_launch(act[0].hi, act[0].lo, feat_out, (long)B * T[0] * C, s);
   // conv 1..n-1 as strided-window GEMMs (+GELU)
   int cur = 0;

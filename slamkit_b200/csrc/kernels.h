@@ -112,7 +112,7 @@ int sk_split_f32_launch(const float* x, bf16* hi, bf16* lo, long n, cudaStream_t
 extern "C" int sk_conv0_nstat(void);
 int sk_conv0_launch(const float* wav, const float* w, const float* gamma, const float* beta, double* stats,
                     float2* affine, bf16* out_hi, bf16* out_lo, int B, int S, int pad, int T0, int C, int KW, int ST,
-                    float eps, cudaStream_t s);
+                    float eps, cudaStream_t s, bf16* bprep = nullptr /* [B][C][64] bf16 scratch: enables the tensor-core front */);
 int sk_layernorm_hilo_launch(const bf16* a_hi, const bf16* a_lo, const bf16* b_hi, const bf16* b_lo, const float* gamma,
                              const float* beta, bf16* o_hi, bf16* o_lo, float* o_f32, int M, int D, float eps,
                              cudaStream_t s);
