@@ -276,12 +276,13 @@ def run_hubert_gpu(args, rank, local_rank, world, lib, dist):
         lib.sk_prof_enable(0)
         conv0_bytes = HUBERT_B * (HUBERT_T0 * 512 * 2 * 2 + (HUBERT_S + 80) * 4)
         gbs = conv0_bytes / (ms[3] / 1e3) / 1e9 if ms[3] > 0 else None
-        out["roofline"] = {"bound": "hbm", "kernel": "conv0_apply_kernel (conv0 + GroupNorm + GELU, hi/lo channels-last)",
+        out["roofline"] = {"bound": "hbm", "kernel": "conv0_tc_kernel (conv0 taps + GroupNorm affine as a split-bf16 tcgen05 GEMM, "
+                                                     "GELU + hi/lo split in the epilogue, channels-last TMA stores)",
                            "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                            "frac": (gbs / pk["hbm_gbs"]) if gbs else None,
-                           # ncu --set full at batch 16: 3.086 GB written + 0.031 GB read per launch -> x4 at batch 64
-                           "traffic": 4 * (3.0860e9 + 0.0315e9), "traffic_unit": "bytes/launch",
-                           "traffic_source": "profiles/r01_ncu_conv0_apply_v4.txt (batch 16, scaled x4)",
+                           # ncu --set full at batch 16: 3.0865 GB written + 0.0326 GB read per launch -> x4 at batch 64
+                           "traffic": 4 * (3.0865e9 + 0.0326e9), "traffic_unit": "bytes/launch",
+                           "traffic_source": "profiles/r02_ncu_conv0_tc.txt (batch 16, scaled x4)",
                            "algorithmic_bytes_per_launch": conv0_bytes, "peak_source": pk["source"],
                            "breakdown_ms": {"gemm": ms[0], "attention": ms[1], "conv0_apply": ms[3],
                                             "batch": dev_ms / n},

@@ -9,5 +9,5 @@ w = (0.1 * torch.randn(16, 480000)).clamp(-1, 1).cuda()
 for _ in range(2): fe.units_device(w, None)
 torch.cuda.synchronize()
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv0_apply -s 1 -c 1 -f -o gpurun_out/prof_conv0_v4 python /tmp/hub_once.py > gpurun_out/ncu_conv0.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv0_tc_kernel -s 1 -c 1 -f -o gpurun_out/prof_conv0_tc python /tmp/hub_once.py > gpurun_out/ncu_conv0.log 2>&1
 tail -1 gpurun_out/ncu_conv0.log
