@@ -33,6 +33,13 @@ def _mk_lm(cfg_o, seed, max_batch, max_seq, device=DEV, trainable=True):
     return m, p
 
 
+def _usable_cpus() -> int:
+    """Threads for the CPU oracle: the affinity mask capped by the cgroup quota (the GPU box shows hundreds of host cores
+    it may not run on; oversubscribing them makes the oracle crawl)."""
+    import bench
+    return bench.usable_cpus()
+
+
 def _tiny_o():
     from oracle import lm_oracle as O
     return O.OracleLMConfig(vocab_size=502, hidden=128, n_layers=2, n_heads=2, n_kv_heads=1, head_dim=64, ffn=256)
@@ -49,7 +56,7 @@ def test_lm_true_width_vs_oracle(n_layers, B, T):
         their independent rounding noise (~1e-2 on the logits after a few layers), so the bar is the principled one -- the
         B200 path must be as close to the fp32 answer as the reference's own bf16 path is (factor 1.3 + a small floor)."""
     from oracle import lm_oracle as O
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(_usable_cpus())
     cfg_o = O.OracleLMConfig(n_layers=n_layers)
     assert (cfg_o.hidden, cfg_o.n_heads, cfg_o.n_kv_heads, cfg_o.ffn, cfg_o.vocab_size) == (896, 14, 2, 4864, 502)
     m, p = _mk_lm(cfg_o, 5, B, T)
@@ -93,7 +100,7 @@ def test_hubert_full_geometry_unit_ids_vs_oracle():
     mismatch is only tolerated on a near-tie (margin below the feature noise)."""
     from oracle import hubert_oracle as HO
     from test_gpu_hubert import _mk
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(_usable_cpus())
     o = HO.OracleHubertConfig()
     assert (o.conv_dim, o.hidden, o.n_heads, o.ffn, o.layer, o.n_units) == (512, 768, 12, 3072, 11, 500)
     S = 160000
