@@ -38,6 +38,30 @@ SK_DEVINL void tmem_st_32(uint32_t taddr, const uint32_t (&r)[32]) {
       : "memory");
 }
 SK_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+SK_DEVINL void tmem_ld_16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// inverse rotary embedding (the backward of apply_rotary_pos_emb) on 8 (x1, x2) pairs held as packed bf16, with the
+// rounding points of the bf16 autograd chain (the same as rope_kernel's inverse mode): o1 = bf16(x1 c) + bf16(x2 s),
+// o2 = bf16(x2 c) + bf16(-x1 s)
+SK_DEVINL void rope_inv8(const uint32_t (&x1)[4], const uint32_t (&x2)[4], const uint4 cv, const uint4 sv, uint4& o1, uint4& o2) {
+  const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw[4] = {sv.x, sv.y, sv.z, sv.w};
+  uint32_t a[4], b[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 p = unpack_bf16(x1[k]), q = unpack_bf16(x2[k]), c = unpack_bf16(cw[k]), sn = unpack_bf16(sw[k]);
+    a[k] = pack_bf16(bf16_round(p.x * c.x) + bf16_round(q.x * sn.x), bf16_round(p.y * c.y) + bf16_round(q.y * sn.y));
+    b[k] = pack_bf16(bf16_round(q.x * c.x) + bf16_round(-p.x * sn.x), bf16_round(q.y * c.y) + bf16_round(-p.y * sn.y));
+  }
+  o1 = make_uint4(a[0], a[1], a[2], a[3]);
+  o2 = make_uint4(b[0], b[1], b[2], b[3]);
+}
 
 template <bool CAUSAL>
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -612,19 +636,24 @@ namespace {
 constexpr int BWD_THREADS = 320;                            // TMA warp, MMA warp, 8 element-wise warps (2 per TMEM quadrant)
 constexpr int BQ_BC = 64;                                   // keys per step in the dQ kernel
 constexpr uint32_t T64_BYTES = 64 * 128;                    // [64 rows][64 dims] bf16 tile
-constexpr uint32_t DQ_SMEM = 2 * SQ_BYTES + 4 * T64_BYTES + SQ_BYTES + 256 + 1024;   // Q, dO, K[2], V[2], dS
+constexpr uint32_t DQ_SMEM = 2 * SQ_BYTES + 4 * T64_BYTES + SQ_BYTES + SQ_BYTES + 1024 + 256 + 1024;   // Q, dO, K[2], V[2], dS, O, delta halves
 
 template <bool CAUSAL>
 __global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
-                      const __grid_constant__ CUtensorMap tmDO, const float* __restrict__ lse,
-                      const float* __restrict__ delta, bf16* __restrict__ dq, int T, int ldg, int H, int KVH, float scale,
-                      const int* __restrict__ seg_start) {
+                      const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmO,
+                      const float* __restrict__ lse, float* __restrict__ delta_out, bf16* __restrict__ dq, int T, int ldg,
+                      int H, int KVH, float scale, const int* __restrict__ seg_start, const bf16* __restrict__ rope_cos,
+                      const bf16* __restrict__ rope_sin, const int* __restrict__ pos_ids, int max_pos) {
+  // This kernel runs FIRST in the backward pass: it also produces delta[b,h,t] = sum_d dO*O for its 128 query rows (the
+  // O tile rides along with Q and dO) and writes it for the dK/dV kernel, and -- when rope tables are given -- applies
+  // the inverse rotary embedding to dQ in its epilogue (no separate delta / rope kernels, no extra pass over dqkv).
   griddep_launch();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base, sdO = sQ + SQ_BYTES, sK = sdO + SQ_BYTES, sV = sK + 2 * T64_BYTES,
-                 sdS = sV + 2 * T64_BYTES, bar = sdS + SQ_BYTES;
+                 sdS = sV + 2 * T64_BYTES, sO = sdS + SQ_BYTES, sDel = sO + SQ_BYTES, bar = sDel + 1024;
+  float* del_ptr = reinterpret_cast<float*>(smem_raw + (sDel - smem_u32(smem_raw)));   // [2 halves][128 rows]
   const uint32_t q_full = bar, k_full = bar + 8, k_empty = bar + 24, v_full = bar + 40, v_empty = bar + 56,
                  sdp_full = bar + 72, sdp_empty = bar + 80, ds_full = bar + 88, ds_empty = bar + 96, dq_done = bar + 104,
                  tmem_slot = bar + 112;
@@ -642,6 +671,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     tma_prefetch_desc(&tmQKV128);
     tma_prefetch_desc(&tmQKV64);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmO);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full + 8 * s, 1);
@@ -672,9 +702,10 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * SQ_BYTES);
+      mbar_arrive_expect_tx(q_full, 3 * SQ_BYTES);
       tma_load_2d(sQ, &tmQKV128, q_full, h * 64, row_base + q0);
       tma_load_2d(sdO, &tmDO, q_full, h * 64, row_base + q0);
+      tma_load_2d(sO, &tmO, q_full, h * 64, row_base + q0);
       for (int j = 0; j < n_it; ++j) {
         const int st = j & 1;
         const uint32_t par = ((j >> 1) & 1) ^ 1u;
@@ -741,7 +772,31 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     // packed-pair math (two keys per instruction): p = 2^(s*sl2 - lse2), dS' = p * (dP - delta); the 1/sqrt(d) factor of
     // dS is applied once to dQ in the epilogue instead of to every score
     const f32x2 nlse2 = dup2(row_ok ? -lse[soff] * 1.4426950408889634f : 0.f);
-    const f32x2 del2 = dup2(row_ok ? delta[soff] : 0.f);
+    // delta of this row: each of the row's two warps sums its 32 dims of dO*O from the swizzled tiles (8 dims per 16-byte
+    // chunk, chunks paired up in a fixed tree), the halves meet through shared memory
+    mbar_wait(q_full, 0);
+    {
+      float pc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((((half * 4 + c) ^ (r & 7))) << 4);
+        uint32_t a[4], g[4];
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(sO + off));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]) : "r"(sdO + off));
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 x = unpack_bf16(a[k]), y = unpack_bf16(g[k]);
+          acc += x.x * y.x + x.y * y.y;
+        }
+        pc[c] = acc;
+      }
+      del_ptr[half * 128 + r] = (pc[0] + pc[1]) + (pc[2] + pc[3]);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float delta_row = del_ptr[r] + del_ptr[128 + r];
+    if (half == 0 && row_ok) delta_out[soff] = delta_row;
+    const f32x2 del2 = dup2(row_ok ? delta_row : 0.f);
     const f32x2 sl22 = dup2(sl2);
     const int lb = (seg_start && row_ok) ? seg_start[row_base + qrow] : 0;   // first visible key of this row
     for (int j = 0; j < n_it; ++j) {
@@ -805,7 +860,33 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     mbar_wait(dq_done, 0);
     tc_fence_after();
     bf16* op = dq + ((size_t)(row_base + qrow)) * ldg + h * 64;
-    {
+    if (rope_cos != nullptr) {
+      // dims [16 half, 16 half + 16) pair with dims 32 further: this warp rotates its 16 pairs
+      uint32_t a[16], b2[16];
+      tmem_ld_16(tdQ + lane_off + half * 16, a);
+      tmem_ld_16(tdQ + lane_off + 32 + half * 16, b2);
+      tmem_ld_wait();
+      if (row_ok) {
+        int pos = pos_ids ? pos_ids[row_base + qrow] : qrow;
+        pos = max(0, min(pos, max_pos - 1));
+        uint32_t x1[8], x2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          x1[i] = pack_bf16(__uint_as_float(a[2 * i]) * scale, __uint_as_float(a[2 * i + 1]) * scale);
+          x2[i] = pack_bf16(__uint_as_float(b2[2 * i]) * scale, __uint_as_float(b2[2 * i + 1]) * scale);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint4 cv = ldg128(rope_cos + (size_t)pos * 32 + half * 16 + u * 8), sv = ldg128(rope_sin + (size_t)pos * 32 + half * 16 + u * 8);
+          const uint32_t p1[4] = {x1[4 * u], x1[4 * u + 1], x1[4 * u + 2], x1[4 * u + 3]};
+          const uint32_t p2[4] = {x2[4 * u], x2[4 * u + 1], x2[4 * u + 2], x2[4 * u + 3]};
+          uint4 o1, o2;
+          rope_inv8(p1, p2, cv, sv, o1, o2);
+          stg128(op + half * 16 + u * 8, o1);
+          stg128(op + 32 + half * 16 + u * 8, o2);
+        }
+      }
+    } else {
       uint32_t v[32];
       tmem_ld_32(tdQ + lane_off + half * 32, v);
       tmem_ld_wait();
@@ -1078,33 +1159,56 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   }
 }
 
-// dk / dv (bf16, column slices of the fused gradient buffer) = sum over the GQA group's query heads, fixed order
+// dk / dv (bf16, column slices of the fused gradient buffer) = sum over the GQA group's query heads, fixed order; with
+// rope tables the inverse rotary embedding is applied to dk on the way out.  16 threads per (b, g, t): threads 0..3 own
+// dk dims [8j, 8j+8) AND [32+8j, 32+8j+8) (a rotation pair), threads 8..15 own 8 dv dims each (4..7 idle).
 __global__ void attn_tc_group_reduce_kernel(const bf16* __restrict__ partial, bf16* __restrict__ dk, bf16* __restrict__ dv,
-                                            int B, int T, int H, int KVH, int ldg) {
+                                            int B, int T, int H, int KVH, int ldg, const bf16* __restrict__ rope_cos,
+                                            const bf16* __restrict__ rope_sin, const int* __restrict__ pos_ids, int max_pos) {
   griddep_launch();
   griddep_wait();
   const int group = H / KVH;
-  const long total = (long)B * KVH * T * 16;      // 16 threads per (b, g, t): 8 columns each of the 128 (dK | dV)
+  const long total = (long)B * KVH * T * 16;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i & 15);
+    if (c8 >= 4 && c8 < 8) continue;
     const long rt = i >> 4;
     const int t = (int)(rt % T);
     const int gg = (int)((rt / T) % KVH);
     const int b = (int)(rt / ((long)T * KVH));
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int j = 0; j < group; ++j) {
-      const uint4 a = ldg128_stream(partial + (((size_t)b * H + gg * group + j) * T + t) * 128 + c8 * 8);
-      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+    auto sum8 = [&](int col, uint32_t (&out)[4]) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < group; ++j) {
+        const uint4 a = ldg128_stream(partial + (((size_t)b * H + gg * group + j) * T + t) * 128 + col);
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16(w[k]);
-        acc[2 * k] += f.x;
-        acc[2 * k + 1] += f.y;
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16(w[k]);
+          acc[2 * k] += f.x;
+          acc[2 * k + 1] += f.y;
+        }
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) out[k] = pack_bf16(acc[2 * k], acc[2 * k + 1]);
+    };
+    if (c8 < 4) {
+      uint32_t x1[4], x2[4];
+      sum8(c8 * 8, x1);
+      sum8(32 + c8 * 8, x2);
+      bf16* dst = dk + ((size_t)b * T + t) * ldg + gg * 64 + c8 * 8;
+      uint4 o1 = make_uint4(x1[0], x1[1], x1[2], x1[3]), o2 = make_uint4(x2[0], x2[1], x2[2], x2[3]);
+      if (rope_cos != nullptr) {
+        int pos = pos_ids ? pos_ids[(size_t)b * T + t] : t;
+        pos = max(0, min(pos, max_pos - 1));
+        rope_inv8(x1, x2, ldg128(rope_cos + (size_t)pos * 32 + c8 * 8), ldg128(rope_sin + (size_t)pos * 32 + c8 * 8), o1, o2);
+      }
+      stg128(dst, o1);
+      stg128(dst + 32, o2);
+    } else {
+      uint32_t x[4];
+      sum8(64 + (c8 - 8) * 8, x);
+      stg128(dv + ((size_t)b * T + t) * ldg + gg * 64 + (c8 - 8) * 8, make_uint4(x[0], x[1], x[2], x[3]));
     }
-    bf16* dst = (c8 < 8 ? dk : dv) + ((size_t)b * T + t) * ldg + gg * 64 + (c8 & 7) * 8;
-    stg128(dst, make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
-                           pack_bf16(acc[6], acc[7])));
   }
 }
 
@@ -1112,19 +1216,21 @@ __global__ void attn_tc_group_reduce_kernel(const bf16* __restrict__ partial, bf
 
 // Backward launcher.  qkv / dqkv share the fused [B*T, ld] layout; delta fp32 [B,H,T] and partial fp32 [B,H,T,128] are
 // caller-provided scratch (delta is filled here).
-int sk_attn_delta_launch(const bf16* o, const bf16* d_o, float* delta, int B, int T, int H, int ldo, cudaStream_t s);
 int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse, float* delta, float* partial_f,
                           bf16* dqkv, int B, int T, int H, int KVH, int ld, int ldo, int ldg, int causal, float scale,
-                          cudaStream_t s, const int* seg_start, const int* seg_end) {
+                          cudaStream_t s, const int* seg_start, const int* seg_end, const bf16* rope_cos,
+                          const bf16* rope_sin, const int* pos_ids, int max_pos) {
   SK_REQUIRE((seg_start == nullptr) == (seg_end == nullptr), "attn_tc_bwd: seg_start and seg_end go together");
   SK_REQUIRE(seg_start == nullptr || causal, "attn_tc_bwd: document segments need the causal kernels");
   SK_REQUIRE(H % KVH == 0, "attention: H must be a multiple of KVH");
-  CUtensorMap tm128, tm64, tmdo128, tmdo64;
+  SK_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr) && (rope_cos == nullptr || max_pos > 0), "attn_tc_bwd: rope tables go together");
+  CUtensorMap tm128, tm64, tmdo128, tmdo64, tmo128;
   int rc;
   if ((rc = sk_make_tmap_2d(&tm128, qkv, 2, (uint64_t)(H + 2 * KVH) * 64, (uint64_t)B * T, (uint64_t)ld, 64, 128))) return rc;
   if ((rc = sk_make_tmap_2d(&tm64, qkv, 2, (uint64_t)(H + 2 * KVH) * 64, (uint64_t)B * T, (uint64_t)ld, 64, 64))) return rc;
   if ((rc = sk_make_tmap_2d(&tmdo128, d_o, 2, (uint64_t)H * 64, (uint64_t)B * T, (uint64_t)ldo, 64, 128))) return rc;
   if ((rc = sk_make_tmap_2d(&tmdo64, d_o, 2, (uint64_t)H * 64, (uint64_t)B * T, (uint64_t)ldo, 64, 64))) return rc;
+  if ((rc = sk_make_tmap_2d(&tmo128, o, 2, (uint64_t)H * 64, (uint64_t)B * T, (uint64_t)ldo, 64, 128))) return rc;
   static bool init = false;
   if (!init) {
     SK_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
@@ -1134,25 +1240,25 @@ int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const
     init = true;
   }
   bf16* partial = reinterpret_cast<bf16*>(partial_f);   // bf16 [B,H,T,128]: uses the first half of the caller's fp32-sized scratch
-  SK_TRY_RC(sk_attn_delta_launch(o, d_o, delta, B, T, H, ldo, s));
+  // dQ first (it also writes delta for the dK/dV kernel), then dK/dV, then the GQA group reduction (+ inverse RoPE on dk)
   sk_prof_begin(1, s);
   dim3 g1(H, B, (T + AT_BC - 1) / AT_BC), g2(H, B, (T + AT_BR - 1) / AT_BR);
   bf16* dq = dqkv;
   bf16* dk = dqkv + H * 64;
   bf16* dv = dqkv + (H + KVH) * 64;
   if (causal) {
-    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dkdv_kernel<true>, dim3(g1), dim3(BWD_THREADS), (size_t)(DKDV_SMEM), s, tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale, seg_start, seg_end));
-    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dq_kernel<true>, dim3(g2), dim3(BWD_THREADS), (size_t)(DQ_SMEM), s, tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale, seg_start));
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dq_kernel<true>, dim3(g2), dim3(BWD_THREADS), (size_t)(DQ_SMEM), s, tm128, tm64, tmdo128, tmo128, lse, delta, dq, T, ldg, H, KVH, scale, seg_start, rope_cos, rope_sin, pos_ids, max_pos));
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dkdv_kernel<true>, dim3(g1), dim3(BWD_THREADS), (size_t)(DKDV_SMEM), s, tm128, tm64, tmdo64, lse, (const float*)delta, partial, T, H, KVH, scale, seg_start, seg_end));
   } else {
-    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dkdv_kernel<false>, dim3(g1), dim3(BWD_THREADS), (size_t)(DKDV_SMEM), s, tm128, tm64, tmdo64, lse, delta, partial, T, H, KVH, scale, seg_start, seg_end));
-    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dq_kernel<false>, dim3(g2), dim3(BWD_THREADS), (size_t)(DQ_SMEM), s, tm128, tm64, tmdo128, lse, delta, dq, T, ldg, H, KVH, scale, seg_start));
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dq_kernel<false>, dim3(g2), dim3(BWD_THREADS), (size_t)(DQ_SMEM), s, tm128, tm64, tmdo128, tmo128, lse, delta, dq, T, ldg, H, KVH, scale, seg_start, rope_cos, rope_sin, pos_ids, max_pos));
+    SK_CUDA_CHECK(sk_launch_pdl(attn_tc_bwd_dkdv_kernel<false>, dim3(g1), dim3(BWD_THREADS), (size_t)(DKDV_SMEM), s, tm128, tm64, tmdo64, lse, (const float*)delta, partial, T, H, KVH, scale, seg_start, seg_end));
   }
   sk_count_launch();
   sk_count_launch();                               // two kernels above; the reduce below is counted by SK_LAUNCH_CHECK
   const long total = (long)B * KVH * T * 16;
   int blocks = (int)((total + 255) / 256);
   if (blocks > sk_num_sms() * 8) blocks = sk_num_sms() * 8;
-  SK_CUDA_CHECK(sk_launch_pdl(attn_tc_group_reduce_kernel, dim3(blocks), dim3(256), (size_t)(0), s, partial, dk, dv, B, T, H, KVH, ldg));
+  SK_CUDA_CHECK(sk_launch_pdl(attn_tc_group_reduce_kernel, dim3(blocks), dim3(256), (size_t)(0), s, (const bf16*)partial, dk, dv, B, T, H, KVH, ldg, rope_cos, rope_sin, pos_ids, max_pos));
   sk_prof_end(s);
   SK_LAUNCH_CHECK();
   return 0;

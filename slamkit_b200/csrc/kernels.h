@@ -103,7 +103,10 @@ int sk_attn_tc_fwd_split_launch(const bf16* qkv_hi, const bf16* qkv_lo, bf16* o_
 // its last -- block-diagonal causal attention for packed batches (sk_seg_bounds_launch builds them from position_ids)
 int sk_attn_tc_bwd_launch(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse, float* delta, float* partial,
                           bf16* dqkv, int B, int T, int H, int KVH, int ld, int ldo, int ldg, int causal, float scale,
-                          cudaStream_t s, const int* seg_start = nullptr, const int* seg_end = nullptr);
+                          cudaStream_t s, const int* seg_start = nullptr, const int* seg_end = nullptr,
+                          // optional: apply the inverse rotary embedding to dq / dk on the way out (bf16 [max_pos, 32] tables)
+                          const bf16* rope_cos = nullptr, const bf16* rope_sin = nullptr, const int* pos_ids = nullptr,
+                          int max_pos = 0);
 int sk_attn_tc_fwd_launch(const bf16* qkv, bf16* o, float* lse, int B, int T, int H, int KVH, int ld, int ldo, int causal,
                           float scale, cudaStream_t s, const int* seg_start = nullptr);
 

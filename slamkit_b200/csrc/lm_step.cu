@@ -301,8 +301,8 @@ int backward_impl(SkLm* lm, const int64_t* ids, const int32_t* pos_ids, int B, i
     SK_TRY(linear_wgrad(M, d, d, dxB, ao, G + o.wo, accumulate, s, lm->ws + w.splitk, (size_t)w.splitk_bytes));
     SK_TRY(sk_attn_tc_bwd_launch(qkv, ao, dao, lse, wsp<float>(lm, w.delta), wsp<float>(lm, w.attn_partial), dqkv, B, T,
                                  lm->H, lm->KVH, Q, d, Q, 1, scale, s, pos_ids ? wsp<int32_t>(lm, w.seg_start) : nullptr,
-                                 pos_ids ? wsp<int32_t>(lm, w.seg_end) : nullptr));
-    SK_TRY(sk_rope_launch(dqkv, lm->rope_cos, lm->rope_sin, pos_ids, M, T, Q, lm->H + lm->KVH, lm->hd, 1, lm->cfg.max_positions, s));
+                                 pos_ids ? wsp<int32_t>(lm, w.seg_end) : nullptr, lm->rope_cos, lm->rope_sin, pos_ids,
+                                 lm->cfg.max_positions));   // inverse RoPE on dq / dk applied by the attention kernels' epilogues
     if (lm->cfg.qkv_bias)
       SK_TRY(sk_colsum_launch(dqkv, G + o.bqkv, wsp<float>(lm, w.colsum_partial), M, Q, Q, accumulate, s));
     SK_TRY(linear_dgrad(M, Q, d, dqkv, P + o.wqkv, dh, s));
