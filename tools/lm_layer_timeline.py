@@ -17,7 +17,9 @@ for row in csv.DictReader(lines):
         d["us"] = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(row.get("Metric Unit", "ns"), 1e-3)
     elif row["Metric Name"].startswith("dram__bytes"):
         d["mb"] = d.get("mb", 0.0) + v * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(row.get("Metric Unit", "byte"), 1e-6)
-seq = [by_id[i] for i in sorted(by_id)][-per_step:]
+allk = [by_id[i] for i in sorted(by_id)]
+start = max(i for i, k in enumerate(allk) if k["name"].startswith("embed_fwd"))   # the last step starts at its embedding gather
+seq = allk[start:]
 names = [s["name"] for s in seq]
 i_ce = max(i for i, n in enumerate(names) if n.startswith("ce_"))
 fwd, bwd = seq[:i_ce - 2], seq[i_ce + 1:]          # forward ends with final rmsnorm + lm_head GEMM before the CE kernels

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 N=$(python tools/lm_one_step.py | awk '/launches per step/{print $4}')
 echo "launches per step: $N"
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-   -k 'regex:gemm_tcgen05|splitk_reduce|attn_|rmsnorm|swiglu|rope|colsum|adamw|sumsq|gradnorm|embed|ce_|add_f32|transpose|seg_bounds|lmhead' \
+   -k 'regex:gemm_tcgen05|splitk_reduce|attn_|rmsnorm|swiglu|rope|colsum|adamw|sumsq|gradnorm|embed|ce_|add_f|transpose|seg_bounds|lmhead' \
    --csv --log-file gpurun_out/lm_launches.csv python tools/lm_one_step.py > gpurun_out/ncu_lm.log 2>&1
 tail -2 gpurun_out/ncu_lm.log
 python tools/summarize_launches.py gpurun_out/lm_launches.csv > gpurun_out/lm_launches_summary.txt
@@ -19,7 +19,8 @@ for r in csv.DictReader(rows):
     d = by.setdefault(int(r["ID"]), {"name": r["Kernel Name"], "b": 0.0})
     if r["Metric Name"].startswith("dram__bytes"):
         d["b"] += float(r["Metric Value"].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[r["Metric Unit"]]
-seq = [by[i] for i in sorted(by)][-per_step:]
+allk = [by[i] for i in sorted(by)]
+seq = allk[max(i for i, k in enumerate(allk) if "embed_fwd" in k["name"]):]
 g = [x["b"] for x in seq if "gemm_tcgen05" in x["name"]]
 json.dump({"gemm_dram_bytes_per_launch": sum(g) / len(g), "gemm_launches_per_step": len(g), "gemm_dram_bytes_per_step": sum(g),
            "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the tcgen05 GEMM launches of one [8,1024] step, tools/profile_lm_step.sh"},
