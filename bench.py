@@ -511,6 +511,8 @@ def main():
     host = [synth_batch(rank, i).pin_memory() for i in range(NB)]
     devb = [h.to(dev) for h in host]
     counts = {"n_items": PER_GPU_BATCH * SEQ, "n_tokens": PER_GPU_BATCH * SEQ}   # labels = ids, none ignored (counted on the host)
+    if os.environ.get("SK_BENCH_NO_HOSTSUM"):        # A/B switch: skip the per-step gloo sum of the counts
+        counts.update({"n_items_global": PER_GPU_BATCH * SEQ * world, "n_tokens_global": PER_GPU_BATCH * SEQ * world})
 
     def step_device(i):
         trainer.train_step([{"input_ids": devb[i % NB], "labels": devb[i % NB], **counts}])

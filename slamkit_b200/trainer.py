@@ -154,7 +154,10 @@ class B200Trainer:
         n_items = sum(int(mb["n_items"]) if "n_items" in mb else int((mb["labels"] != -100).sum()) for mb in micro_batches)
         n_tok = sum(int(mb["n_tokens"]) if "n_tokens" in mb else
                     count_tokens(mb["labels"], self.min_token_id_count, self.max_token_id_count) for mb in micro_batches)
-        n_items, n_tok = self.host.sum([n_items, n_tok])
+        if "n_items_global" in micro_batches[0]:     # counts already summed over ranks by the caller (fixed-shape synthetic runs)
+            n_items, n_tok = float(micro_batches[0]["n_items_global"]), float(micro_batches[0]["n_tokens_global"])
+        else:
+            n_items, n_tok = self.host.sum([n_items, n_tok])
         self.num_input_tokens_seen += int(n_tok)
         loss = torch.zeros((), device=self.model.device)
         for i, mb in enumerate(micro_batches):
