@@ -23,6 +23,7 @@ from slamkit_b200.audio_io import audio_num_frames, load_audio  # noqa: E402
 from slamkit_b200.config import load_config, require  # noqa: E402
 
 logger = logging.getLogger(__name__)
+LAST_STATS = {}     # throughput of the most recent main() call (extraction loop only: no model construction)
 
 
 def build_tokeniser(cfg, device: str, max_batch=None):
@@ -156,8 +157,11 @@ def main(argv=None):
     batches = [files[i:i + cfg.batch_size] for i in range(0, len(files), cfg.batch_size)]
     mine = [b for bi, b in enumerate(batches) if bi % world == rank]      # whole batches round-robin (ids depend on batch composition)
     sizes = []
+    import time
+    t_loop, n_samples = time.perf_counter(), 0
     with open(out_path, "a+") as out_file:
         for batch, wav, lens in BatchPrefetcher(mine, cfg.sample_rate, device, num_workers=cfg.get("num_workers", 4) or 1):
+            n_samples += sum(n for _, n in batch)
             reps = tokeniser.audio_represent(wav, lens)
             lines = []
             for (f, _), rep in zip(batch, reps):
@@ -165,6 +169,11 @@ def main(argv=None):
                 lines.append(json.dumps(rec) + "\n")
             out_file.writelines(lines)
             sizes.append(len(batch))
+    dt = time.perf_counter() - t_loop
+    LAST_STATS.update({"files": sum(sizes), "seconds": dt, "audio_hours": n_samples / cfg.sample_rate / 3600.0,
+                       "audio_hours_per_s": n_samples / cfg.sample_rate / 3600.0 / max(dt, 1e-9)})
+    logger.info(f"rank {rank}: {LAST_STATS['files']} files, {LAST_STATS['audio_hours']:.2f} audio-hours in {dt:.2f} s "
+                f"({LAST_STATS['audio_hours_per_s']:.2f} audio-hours/s: decode + copy + extraction + jsonl)")
     if world > 1:
         import torch.distributed as dist
         json.dump(sizes, open(out_path + ".batches", "w"))
