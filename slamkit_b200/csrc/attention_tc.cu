@@ -13,6 +13,7 @@
 #include "kernels.h"
 #include <cudaTypedefs.h>
 #include <stdlib.h>
+#include <type_traits>
 #define SK_TRY_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 namespace {
@@ -822,19 +823,19 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         }
       }
       uint32_t pk[16];
-      if (mode == 2) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      } else {
+      // one straight-line instance of the 16-pair loop per mode (a mode test inside the unrolled loop leaves a branch per
+      // pair in the SASS and keeps the scheduler from interleaving the pairs' MUFU / FMA chains)
+      auto body = [&](auto mode_c) {
+        constexpr int MODE = decltype(mode_c)::value;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float x0, x1;
           upk2(fma2(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl22, nlse2), x0, x1);
           float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-          if (mode == 1) {
+          if (MODE == 1) {
             if (2 * i > lane) p0 = 0.f;
             if (2 * i + 1 > lane) p1 = 0.f;
-          } else if (mode == 3) {
+          } else if (MODE == 3) {
             const int key = k0 + half * 32 + 2 * i;
             if (!row_ok || key >= T || (CAUSAL && key > qrow) || key < lb) p0 = 0.f;
             if (!row_ok || key + 1 >= T || (CAUSAL && key + 1 > qrow) || key + 1 < lb) p1 = 0.f;
@@ -843,6 +844,13 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           upk2(mul2(pk2(p0, p1), sub2(pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])), del2)), d0, d1);
           pk[i] = pack_bf16(d0, d1);
         }
+      };
+      if (mode == 0) body(std::integral_constant<int, 0>{});
+      else if (mode == 1) body(std::integral_constant<int, 1>{});
+      else if (mode == 3) body(std::integral_constant<int, 3>{});
+      else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
       }
       mbar_wait(ds_empty, (j & 1) ^ 1u);         // previous dQ MMA finished reading the dS buffer (the math above overlaps it)
 #pragma unroll
@@ -1072,36 +1080,38 @@ attn_tc_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       }
       uint32_t pp[16], pd[16];
       // packed-pair math (two queries per instruction); dS'^T omits the 1/sqrt(d) factor, applied to dK in the epilogue
-      if (mode == 2) {
+      // one straight-line instance of the 16-pair loop per mode (see the dQ kernel)
+      auto body = [&](auto mode_c) {
+        constexpr int MODE = decltype(mode_c)::value;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int qi = half * 32 + 2 * e;
+          const f32x2 nl2 = *reinterpret_cast<const f32x2*>(st_lse + qi);
+          const f32x2 dl = *reinterpret_cast<const f32x2*>(st_lse + 64 + qi);
+          float x0, x1;
+          upk2(fma2(pk2(__uint_as_float(sv[2 * e]), __uint_as_float(sv[2 * e + 1])), sl22, nl2), x0, x1);
+          float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          if (MODE == 1) {
+            if (lane > 2 * e) p0 = 0.f;
+            if (lane > 2 * e + 1) p1 = 0.f;
+          } else if (MODE == 3) {
+            const int qrow = q0 + qi;
+            const int2 sg = *reinterpret_cast<const int2*>(st_lse + 128 + qi);     // first visible key of the two queries
+            if (key >= T || qrow >= T || (CAUSAL && key > qrow) || key < sg.x) p0 = 0.f;
+            if (key >= T || qrow + 1 >= T || (CAUSAL && key > qrow + 1) || key < sg.y) p1 = 0.f;
+          }
+          pp[e] = pack_bf16(p0, p1);
+          float d0, d1;
+          upk2(mul2(pk2(p0, p1), sub2(pk2(__uint_as_float(dv[2 * e]), __uint_as_float(dv[2 * e + 1])), dl)), d0, d1);
+          pd[e] = pack_bf16(d0, d1);
+        }
+      };
+      if (mode == 0) body(std::integral_constant<int, 0>{});
+      else if (mode == 1) body(std::integral_constant<int, 1>{});
+      else if (mode == 3) body(std::integral_constant<int, 3>{});
+      else {
 #pragma unroll
         for (int e = 0; e < 16; ++e) pp[e] = pd[e] = 0u;
-      } else {
-#pragma unroll
-        for (int e2 = 0; e2 < 8; ++e2) {
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int e = 2 * e2 + u;
-            const int qi = half * 32 + 2 * e;
-            const f32x2 nl2 = *reinterpret_cast<const f32x2*>(st_lse + qi);
-            const f32x2 dl = *reinterpret_cast<const f32x2*>(st_lse + 64 + qi);
-            float x0, x1;
-            upk2(fma2(pk2(__uint_as_float(sv[2 * e]), __uint_as_float(sv[2 * e + 1])), sl22, nl2), x0, x1);
-            float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            if (mode == 1) {
-              if (lane > 2 * e) p0 = 0.f;
-              if (lane > 2 * e + 1) p1 = 0.f;
-            } else if (mode == 3) {
-              const int qrow = q0 + qi;
-              const int2 sg = *reinterpret_cast<const int2*>(st_lse + 128 + qi);     // first visible key of the two queries
-              if (key >= T || qrow >= T || (CAUSAL && key > qrow) || key < sg.x) p0 = 0.f;
-              if (key >= T || qrow + 1 >= T || (CAUSAL && key > qrow + 1) || key < sg.y) p1 = 0.f;
-            }
-            pp[e] = pack_bf16(p0, p1);
-            float d0, d1;
-            upk2(mul2(pk2(p0, p1), sub2(pk2(__uint_as_float(dv[2 * e]), __uint_as_float(dv[2 * e + 1])), dl)), d0, d1);
-            pd[e] = pack_bf16(d0, d1);
-          }
-        }
       }
       mbar_wait(pds_empty, (i & 1) ^ 1u);        // previous dV / dK MMAs finished reading P^T / dS^T (overlapped by the math)
 #pragma unroll
