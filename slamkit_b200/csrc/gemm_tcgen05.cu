@@ -724,6 +724,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             stage_store(&tmC, pk, col64);
           }
+        } else if (p.tma_store && !p.bias && !p.residual && !p.act) {
+          // plain convert-and-store (dgrads, wgrads, gate/up ...): a straight-line instance without the per-column-group
+          // bias / activation / residual tests of the general path below
+#pragma unroll 1
+          for (int c2 = chalf * (BN / 64 / CS); c2 < (chalf + 1) * (BN / 64 / CS); ++c2) {
+            uint32_t r0[32], r1[32], pk[32];
+            tmem_ld_32x32(taddr + c2 * 64, r0);
+            tmem_ld_32x32(taddr + c2 * 64 + 32, r1);
+            tmem_ld_wait();
+            if (SK && n_contrib > 0) {
+              sk_fixup_add(r0, p.sk_ws, c2 * 2, row_in_tile, first_contrib, w.G, n_contrib);
+              sk_fixup_add(r1, p.sk_ws, c2 * 2 + 1, row_in_tile, first_contrib, w.G, n_contrib);
+            }
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              pk[t] = pack_bf16(__uint_as_float(r0[2 * t]), __uint_as_float(r0[2 * t + 1]));
+              pk[16 + t] = pack_bf16(__uint_as_float(r1[2 * t]), __uint_as_float(r1[2 * t + 1]));
+            }
+            stage_store(&tmC, pk, n0 + c2 * 64);
+          }
         } else if (p.tma_store) {
           // coalesced path: TMEM -> registers -> 128B-swizzled smem (this warp's private 32-row buffer) -> TMA store
 #pragma unroll 1
