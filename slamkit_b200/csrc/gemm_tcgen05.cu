@@ -702,8 +702,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v0[i] = __uint_as_float(r0[g * 8 + i]);
                 v1[i] = __uint_as_float(r1[g * 8 + i]);
               }
-              epi_bias_act(v0, p, col64 + g * 8);
-              epi_bias_act(v1, p, col64 + 32 + g * 8);
+              if (p.bias) {                                   // bf16 bias (the QKV projection's), no activation on this path
+                const uint4 b0 = ldg128(reinterpret_cast<const bf16*>(p.bias) + col64 + g * 8);
+                const uint4 b1 = ldg128(reinterpret_cast<const bf16*>(p.bias) + col64 + 32 + g * 8);
+                const uint32_t w0[4] = {b0.x, b0.y, b0.z, b0.w}, w1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f0 = unpack_bf16(w0[e]), f1 = unpack_bf16(w1[e]);
+                  v0[2 * e] += f0.x; v0[2 * e + 1] += f0.y;
+                  v1[2 * e] += f1.x; v1[2 * e + 1] += f1.y;
+                }
+              }
               if (col64 < p.rope_cols) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -743,6 +752,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               pk[16 + t] = pack_bf16(__uint_as_float(r1[2 * t]), __uint_as_float(r1[2 * t + 1]));
             }
             stage_store(&tmC, pk, n0 + c2 * 64);
+          }
+        } else if (p.tma_store && !p.bias && !p.act && p.residual && !p.residual_lo) {
+          // residual add only (o-proj and down-proj forward: x + linear(..), rounded like the unfused bf16 graph): the
+          // row's 128 residual bytes are requested before the accumulator is read; straight-line
+#pragma unroll 1
+          for (int c2 = chalf * (BN / 64 / CS); c2 < (chalf + 1) * (BN / 64 / CS); ++c2) {
+            const int col64 = n0 + c2 * 64;
+            if (col64 >= p.N) break;
+            uint4 rv[8];
+            if (row_ok) {
+              const bf16* rp = p.residual + row * p.ldr + col64;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rv[j] = (col64 + 8 * j < p.N) ? ldg128(rp + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rv[j] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            uint32_t r0[32], r1[32], pk[32];
+            tmem_ld_32x32(taddr + c2 * 64, r0);
+            tmem_ld_32x32(taddr + c2 * 64 + 32, r1);
+            tmem_ld_wait();
+            if (SK && n_contrib > 0) {
+              sk_fixup_add(r0, p.sk_ws, c2 * 2, row_in_tile, first_contrib, w.G, n_contrib);
+              sk_fixup_add(r1, p.sk_ws, c2 * 2 + 1, row_in_tile, first_contrib, w.G, n_contrib);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t* r = j < 4 ? r0 + 8 * j : r1 + 8 * (j - 4);
+              const uint32_t rw[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16(rw[e]);
+                float a0 = __uint_as_float(r[2 * e]), a1 = __uint_as_float(r[2 * e + 1]);
+                if (p.round_before_res) {
+                  const float2 t = unpack_bf16(pack_bf16(a0, a1));
+                  a0 = t.x; a1 = t.y;
+                }
+                pk[4 * j + e] = pack_bf16(a0 + f.x, a1 + f.y);
+              }
+            }
+            stage_store(&tmC, pk, col64);
           }
         } else if (p.tma_store) {
           // coalesced path: TMEM -> registers -> 128B-swizzled smem (this warp's private 32-row buffer) -> TMA store
@@ -1122,8 +1172,9 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
       SK_REQUIRE(BN == 256 && g.N % 128 == 0 && g.aux && g.ld_aux % 8 == 0 && !g.bias,
                  "gemm: SwiGLU-backward epilogue needs N = F with F %% 128 == 0 and the saved gu activation");
     } else if (g.epi == 3) {
-      SK_REQUIRE(g.rope_cos && g.rope_sin && g.rope_T > 0 && g.rope_maxpos > 0 && g.rope_cols % 64 == 0 && g.N % 64 == 0,
-                 "gemm: RoPE epilogue needs cos/sin tables and 64-column heads");
+      SK_REQUIRE(g.rope_cos && g.rope_sin && g.rope_T > 0 && g.rope_maxpos > 0 && g.rope_cols % 64 == 0 && g.N % 64 == 0 &&
+                     !g.bias_f32,
+                 "gemm: RoPE epilogue needs cos/sin tables, 64-column heads and a bf16 bias");
     } else {
       SK_REQUIRE(false, "gemm: unknown fused epilogue %d", g.epi);
     }
