@@ -647,7 +647,8 @@ def main():
         line = {"metric": "speech-tokens/sec (SLAM seq=1024)", "value": value, "unit": "tokens/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {**workload_config(world), "api": "slamkit_b200.trainer.B200Trainer.train_step"},
+                "config": {**workload_config(world), "api": "slamkit_b200.trainer.B200Trainer.train_step",
+                           "dp_comm": trainer.sync.backend},
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": PER_GPU_BATCH * SEQ * 8,
                         "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},

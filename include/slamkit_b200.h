@@ -267,6 +267,37 @@ int sk_flac_info(const char* path, int32_t* sample_rate, int32_t* channels, int3
 /* interleaved int32 PCM into a host buffer with room for `capacity` samples per channel */
 int sk_flac_decode_i32(const char* path, int32_t* pcm_host, int64_t capacity, int64_t* n_decoded);
 
+/* ---- data-parallel gradient all-reduce over NVLink peer memory (single NVSwitch node) ----------------------------------
+ * Replaces the per-bucket NCCL all-reduce of accelerate's DDP wrapper around `training_step` (HF:trainer.py:1867-2014;
+ * config/training_args/default.yaml:18) for ranks that share a node: every rank maps every other rank's flat bf16
+ * gradient buffer and a small flag array with CUDA IPC, and one small-footprint kernel per bucket (64-thread CTAs, no
+ * shared memory: they co-reside with the GEMM / attention CTAs of the backward pass) reduce-scatters and all-gathers in
+ * one pass -- rank r sums the W copies of its 1/W of the bucket in rank order (fp32, one rounding: bit-identical on all
+ * ranks) and stores the result into all W buffers.  Protocol per bucket (all on one side stream):
+ *   sk_p2p_signal(slot, epoch)  this rank's gradients of the bucket are final (READY flag to every peer)
+ *   sk_p2p_allreduce_bf16(...)  waits for every peer's READY, reduces, tells every peer when its share is written
+ *   sk_p2p_wait(slots, epoch)   returns (in stream order) when every peer's share of those slots has arrived in this
+ *                               rank's buffer (one call may cover all buckets of a step)
+ * `epoch` must grow by one per reduction of a slot; flags are never reset.  `bufs` / `flags`: arrays of `world` device
+ * pointers (own memory at [rank], IPC mappings elsewhere); ranges in bf16 elements, multiples of 8.  `err_flag`: int in
+ * pinned host memory, set non-zero when a spin timed out (a peer died): check it after synchronising. */
+int64_t sk_p2p_flag_bytes(void);
+int sk_p2p_alloc(int64_t bytes, void** out);                 /* zeroed cudaMalloc (flag arrays) */
+int sk_p2p_free(void* p);
+int sk_p2p_export(const void* ptr, void* handle64, int64_t* offset);   /* IPC handle of the allocation holding ptr */
+int sk_p2p_open(const void* handle64, void** base);
+int sk_p2p_close(void* base);
+int sk_p2p_signal(void* const* flags, int rank, int world, int slot, uint32_t epoch, void* stream);
+int sk_p2p_allreduce_bf16(void* const* bufs, void* const* flags, int rank, int world, int64_t offset_elems, int64_t n_elems,
+                          int slot, uint32_t epoch, int ctas, int* err_flag, void* stream);
+int sk_p2p_wait(void* const* flags, int rank, int world, int slot_lo, int n_slots, uint32_t epoch, int* err_flag, void* stream);
+/* Profiling hook: uint64 [257][4] device buffer that the kernels above fill with %globaltimer stamps per slot (0 READY sent,
+ * 1 reduce kernel running, 2 peers ready, 3 last CTA done; row 256: wait kernel start / end); NULL switches it off. */
+int sk_p2p_set_trace(void* buf);
+/* Test hook: `ctas` CTAs with the reduce kernel's footprint (64 threads, <= 64 registers, no shared memory) that hold their
+ * slot for `ns` nanoseconds; started_u32 counts the CTAs that got onto an SM (tools/coresidency_check.py). */
+int sk_p2p_debug_hog(int ctas, int64_t ns, void* started_u32, void* stream);
+
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 int64_t sk_launch_count(void);
 /* Bench-only device timing: when enabled, CUDA events are recorded on the launching stream around every launch of

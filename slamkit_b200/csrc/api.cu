@@ -206,3 +206,32 @@ int sk_adamw_step(void* params, const void* grads, void* exp_avg, void* exp_avg_
 }
 
 }  // extern "C"
+
+// ---- peer-memory gradient all-reduce (p2p_comm.cu) ------------------------------------------------------------------
+int64_t sk_p2p_flag_bytes(void) { return (int64_t)sk_p2p_flag_bytes_impl(); }
+int sk_p2p_set_trace(void* buf) { return sk_p2p_set_trace_impl(buf); }
+int sk_p2p_debug_hog(int ctas, int64_t ns, void* started_u32, void* stream) {
+  return sk_p2p_hog_launch(ctas, (long long)ns, reinterpret_cast<unsigned*>(started_u32), S(stream));
+}
+int sk_p2p_alloc(int64_t bytes, void** out) { return sk_p2p_alloc_impl((size_t)bytes, out); }
+int sk_p2p_free(void* p) { return sk_p2p_free_impl(p); }
+int sk_p2p_export(const void* ptr, void* handle64, int64_t* offset) {
+  size_t off = 0;
+  const int rc = sk_p2p_export_impl(ptr, handle64, &off);
+  if (offset) *offset = (int64_t)off;
+  return rc;
+}
+int sk_p2p_open(const void* handle64, void** base) { return sk_p2p_open_impl(handle64, base); }
+int sk_p2p_close(void* base) { return sk_p2p_close_impl(base); }
+int sk_p2p_signal(void* const* flags, int rank, int world, int slot, uint32_t epoch, void* stream) {
+  return sk_p2p_signal_launch(flags, rank, world, slot, epoch, S(stream));
+}
+int sk_p2p_wait(void* const* flags, int rank, int world, int slot_lo, int n_slots, uint32_t epoch, int* err_flag, void* stream) {
+  return sk_p2p_wait_launch(flags, rank, world, slot_lo, n_slots, epoch, err_flag, S(stream));
+}
+int sk_p2p_allreduce_bf16(void* const* bufs, void* const* flags, int rank, int world, int64_t offset_elems, int64_t n_elems,
+                          int slot, uint32_t epoch, int ctas, int* err_flag, void* stream) {
+  SK_REQUIRE(offset_elems >= 0 && n_elems > 0, "p2p_allreduce: bad range");
+  return sk_p2p_allreduce_launch(bufs, flags, rank, world, (size_t)offset_elems, (size_t)n_elems, slot, epoch, ctas, err_flag,
+                                 S(stream));
+}

@@ -289,7 +289,9 @@ SK_DEVINL void sk_fixup_add(uint32_t (&r)[32], const float* ws, int chunk, int r
 }
 
 template <int BN, bool A_MN, bool B_MN, bool SK, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+// register caps: two (EW = 4) or three (EW = 8) warps of this kernel share an SM sub-partition's 16 K registers; 240 /
+// 160 leave the 1024 that one warp of the peer all-reduce kernel needs (p2p_comm.cu), so it can run alongside
+__global__ void __launch_bounds__(64 + 32 * EW, 1) __maxnreg__(EW == 8 ? 160 : 240)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, GemmParams p) {
@@ -1128,7 +1130,9 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
   p.splits = 1;
   p.splitk_ws = nullptr;
   const int num_kb = (g.K + BK - 1) / BK;
-  if (g.splitk_ws && g.batch == 1 && g.passes == 1 && !g.out_f32 && !g.bias && !g.act && !g.C_lo && g.col_gin == 0 &&
+  static const int splitk_env = [] { const char* e = getenv("SK_SPLITK"); return e ? atoi(e) : 1; }();
+  static const int sk_ranges = [] { const char* e = getenv("SK_STREAMK_RANGES"); return e ? atoi(e) : 4; }();
+  if (splitk_env && g.splitk_ws && g.batch == 1 && g.passes == 1 && !g.out_f32 && !g.bias && !g.act && !g.C_lo && g.col_gin == 0 &&
       (g.residual == nullptr || g.residual == g.C) && tiles * 2 <= nsm && num_kb >= 16) {
     int sp = (int)(nsm / tiles);
     if (sp > 8) sp = 8;
@@ -1197,7 +1201,7 @@ int sk_gemm_ex_launch(const SkGemmEx& g, cudaStream_t stream) {
     const long slots = ((long)(units + n_groups - 1) / n_groups) * n_groups;
     if (n_groups >= 1 && rem != 0 && (slots - units) * 100 >= slots * sk_min_idle) {   // enough SM-time would idle
       p.sk_units = rem;
-      p.sk_groups = n_groups < rem * 4 ? n_groups : rem * 4;            // a unit is cut into at most ~4 ranges
+      p.sk_groups = n_groups < rem * sk_ranges ? n_groups : rem * sk_ranges;            // a unit is cut into at most ~4 ranges
       p.sk_G = G;
       p.sk_colunits = colunits;
       p.units = units;

@@ -127,3 +127,17 @@ int sk_rle_launch(const int32_t* labels, const int32_t* n_frames, int32_t* units
                   int B, int T, cudaStream_t s);
 int sk_rel_len_launch(const int64_t* lens, int32_t* n_frames, int B, int S, int T, cudaStream_t s);
 int sk_hilo_to_f32_launch(const bf16* hi, const bf16* lo, float* out, long n, cudaStream_t s);
+
+// p2p_comm.cu: bf16 gradient all-reduce over CUDA-IPC peer memory (one NVSwitch node)
+size_t sk_p2p_flag_bytes_impl();
+int sk_p2p_set_trace_impl(void* buf);
+int sk_p2p_hog_launch(int ctas, long long ns, unsigned* started, cudaStream_t s);
+int sk_p2p_alloc_impl(size_t bytes, void** out);
+int sk_p2p_free_impl(void* p);
+int sk_p2p_export_impl(const void* ptr, void* handle64, size_t* offset);
+int sk_p2p_open_impl(const void* handle64, void** base);
+int sk_p2p_close_impl(void* base);
+int sk_p2p_signal_launch(void* const* flags, int rank, int world, int slot, uint32_t epoch, cudaStream_t s);
+int sk_p2p_wait_launch(void* const* flags, int rank, int world, int slot_lo, int n_slots, uint32_t epoch, int* err_flag, cudaStream_t s);
+int sk_p2p_allreduce_launch(void* const* bufs, void* const* flags, int rank, int world, size_t offset_elems, size_t n_elems,
+                            int slot, uint32_t epoch, int ctas, int* err_flag, cudaStream_t s);

@@ -14,6 +14,7 @@ and summed over ranks through a gloo group, so no step of the loop waits for the
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -42,7 +43,8 @@ def plan_buckets(layer_start: Sequence[int], n_params: int, layers_per_bucket: i
 class GradSync:
     """Sum the flat gradient buffer over the data-parallel ranks (bucketed; overlapped with backward on CUDA)."""
 
-    def __init__(self, model, layers_per_bucket: int = 4, overlap: bool = True, group=None):
+    def __init__(self, model, layers_per_bucket: Optional[int] = None, overlap: bool = True, group=None,
+                 comm: Optional[str] = None):
         import torch.distributed as dist
         self.dist = dist
         self.model = model
@@ -51,35 +53,83 @@ class GradSync:
         nl = model.config.n_layers
         t = model.tensors
         self.layer_start = [t[f"layers.{l}.ln1"][0] for l in range(nl)] + [t["final_norm"][0]]
+        # backend: "p2p" = own kernels over CUDA-IPC peer memory (ranks on one NVSwitch node; p2p.PeerAllReduce), "nccl" =
+        # torch.distributed all_reduce.  All ranks must agree, so a rank that cannot map its peers makes everyone use NCCL.
+        want = (comm or os.environ.get("SK_DP_COMM", "p2p")).lower()
+        assert want in ("p2p", "nccl"), want
+        self.p2p = None
+        self.backend = "nccl" if self.world > 1 else "none"
+        if want == "p2p" and self.world > 1 and model.grads is not None and model.grads.is_cuda:
+            why = ""
+            try:
+                from .p2p import PeerAllReduce
+                self.p2p = PeerAllReduce(model.grads, group)
+            except (L.SkError, RuntimeError, AssertionError) as e:   # noqa: PERF203
+                why = f"{type(e).__name__}: {e}"
+            ok = torch.tensor([1 if self.p2p is not None else 0], device=model.device, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok) == 1:
+                self.backend = "p2p"
+            else:
+                self.p2p = None
+                if dist.get_rank(group) == 0 or why:
+                    print(f"[slamkit_b200] peer-memory all-reduce unavailable ({why or 'a peer could not map this rank'}); using NCCL", flush=True)
+        if layers_per_bucket is None:
+            layers_per_bucket = 2 if self.backend == "p2p" else 4
         self.buckets, self.tail = plan_buckets(self.layer_start, model.n_params, layers_per_bucket)
+        # CTAs of the reduce kernel: few while the backward pass still owns the SMs, many for the ranges that complete last
+        self.ctas_overlap = int(os.environ.get("SK_P2P_CTAS", "148"))
+        self.ctas_tail = int(os.environ.get("SK_P2P_TAIL_CTAS", "1184"))
         self.overlap = bool(overlap) and self.world > 1 and model.grads is not None and model.grads.is_cuda
         self.events: List[torch.cuda.Event] = []
         if self.overlap:
-            self.comm = torch.cuda.Stream(device=model.device)
+            # high priority: the reduce kernel's small CTAs are placed as soon as an SM has room for them
+            prio = -1 if os.environ.get("SK_COMM_PRIO", "1") != "0" else 0
+            self.comm = torch.cuda.Stream(device=model.device, priority=prio)
             self.events = [torch.cuda.Event() for _ in range(nl + 1)]
             for e in self.events:
                 e.record()                      # forces creation of the underlying cudaEvent_t
             arr = (C.c_void_p * (nl + 1))(*[C.c_void_p(e.cuda_event) for e in self.events])
             L.check(model.lib.sk_lm_set_backward_events(model._h, arr, nl + 1))
 
+    def _one(self, lo: int, hi: int, last: bool) -> None:
+        """All-reduce elements [lo, hi) of the flat gradient buffer on the current stream."""
+        if hi <= lo:
+            return
+        if self.p2p is not None and self.p2p.supports(lo, hi):
+            self.p2p.all_reduce(lo, hi, self.ctas_tail if last else self.ctas_overlap)
+        else:
+            self.dist.all_reduce(self.model.grads[lo:hi], group=self.group)
+
     def reduce(self) -> None:
         """Call right after `forward_backward` of the LAST micro-batch of the accumulation window has been enqueued."""
         if self.world == 1:
             return
-        g = self.model.grads
+        if self.p2p is not None:
+            self.p2p.begin()
+        nb = len(self.buckets)
         if not self.overlap:
-            for _, lo, hi in self.buckets:
-                self.dist.all_reduce(g[lo:hi], group=self.group)
-            self.dist.all_reduce(g[self.tail[0]:self.tail[1]], group=self.group)
+            for k, (_, lo, hi) in enumerate(self.buckets):
+                self._one(lo, hi, True)
+            self._one(self.tail[0], self.tail[1], True)
+            if self.p2p is not None:
+                self.p2p.finish()
             return
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(self.comm):
-            for ev_idx, lo, hi in self.buckets:
+            for k, (ev_idx, lo, hi) in enumerate(self.buckets):
                 self.comm.wait_event(self.events[ev_idx])
-                self.dist.all_reduce(g[lo:hi], group=self.group)
+                self._one(lo, hi, k == nb - 1)
             self.comm.wait_stream(cur)
-            self.dist.all_reduce(g[self.tail[0]:self.tail[1]], group=self.group)
+            self._one(self.tail[0], self.tail[1], True)
+            if self.p2p is not None:
+                self.p2p.finish()
         cur.wait_stream(self.comm)
+
+    def check(self) -> None:
+        """Raise if a peer-memory reduction of an earlier step timed out (host flag; no device synchronisation)."""
+        if self.p2p is not None:
+            self.p2p.check()
 
 
 class HostReducer:
@@ -122,10 +172,10 @@ class B200Trainer:
     def __init__(self, model: B200UnitLM, lr: float = 1e-3, min_lr: float = 5e-5, warmup_steps: int = 100,
                  total_steps: int = 17625, max_grad_norm: float = 0.5, weight_decay: float = 0.0,
                  grad_accum: int = 1, overlap_comm: bool = True, min_token_id_count: Optional[int] = None,
-                 max_token_id_count: Optional[int] = None):
+                 max_token_id_count: Optional[int] = None, dp_comm: Optional[str] = None):
         self.model = model
         self.opt = B200AdamW(model, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
-        self.sync = GradSync(model, overlap=overlap_comm)
+        self.sync = GradSync(model, overlap=overlap_comm, comm=dp_comm)
         self.host = HostReducer()
         self.lr, self.min_lr, self.warmup, self.total = lr, min_lr, warmup_steps, total_steps
         self.grad_accum = grad_accum

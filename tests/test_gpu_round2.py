@@ -296,10 +296,12 @@ def _dp_worker(rank, world, port, out_dir):
     labels[full == 0] = -100
     mine = slice(2 * rank, 2 * rank + 2)
     res = {}
-    for overlap in (False, True):
+    for overlap, comm in ((False, "nccl"), (True, "nccl"), (False, "p2p"), (True, "p2p")):
         m, _ = _mk_lm(cfg_o, 11, 2 * world, 96, device=dev)
-        tr = B200Trainer(m, lr=1e-12, min_lr=0.0, warmup_steps=0, total_steps=4, overlap_comm=overlap)   # lr ~0: weights stay put
+        tr = B200Trainer(m, lr=1e-12, min_lr=0.0, warmup_steps=0, total_steps=4, overlap_comm=overlap, dp_comm=comm)   # lr ~0: weights stay put
         assert tr.sync.world == world and tr.sync.overlap == overlap
+        # the peer-memory all-reduce (csrc/p2p_comm.cu) must really be the one that runs -- no silent NCCL fallback here
+        assert tr.sync.backend == comm, (tr.sync.backend, comm)
         # (1) the reduced flat gradient == the sum of the all-gathered per-rank gradients, bit for bit
         n_glob = float((labels != -100).sum())
         m.forward_backward(full[mine], labels[mine], num_items_in_batch=n_glob)
@@ -316,16 +318,23 @@ def _dp_worker(rank, world, port, out_dir):
         for x in gathered[1:]:
             want = (want + x.float())
         # NCCL sums bf16 pairwise in the same order for 2 ranks; for more ranks compare within bf16 rounding of the sum
-        if world == 2:
+        # (the peer-memory kernel adds in rank order in fp32 and rounds once: exactly `want` for any number of ranks)
+        if world == 2 or comm == "p2p":
             bad = (m.grads != want.to(torch.bfloat16)).nonzero().flatten()
-            assert bad.numel() == 0, (f"overlap={overlap}: {bad.numel()} of {m.grads.numel()} elements differ, first {int(bad[0])}, last {int(bad[-1])}; "
+            assert bad.numel() == 0, (f"overlap={overlap} comm={comm}: {bad.numel()} of {m.grads.numel()} elements differ, first {int(bad[0])}, last {int(bad[-1])}; "
                                       f"buckets {tr.sync.buckets} tail {tr.sync.tail}; max abs diff {float((m.grads.float() - want).abs().max())}")
         else:
             assert rel_err(m.grads.float().cpu(), want.cpu()) < 4e-3
         # (2) N-rank loss == 1-rank loss on the concatenated batch (HF average_tokens_across_devices semantics)
-        tr.train_step([{"input_ids": full[mine], "labels": labels[mine]}])
-        res[f"loss_dp_{overlap}"] = tr.reduced_loss()
-        res[f"tokens_{overlap}"] = tr.num_input_tokens_seen
+        # every rank holds the same bits after the reduction
+        same = [torch.empty_like(m.grads) for _ in range(world)]
+        dist.all_gather(same, m.grads)
+        assert all(torch.equal(same[0], x) for x in same[1:]), f"ranks disagree after the {comm} reduction"
+        for _ in range(3):                       # a few real steps: flags / epochs carry over from step to step
+            tr.train_step([{"input_ids": full[mine], "labels": labels[mine]}])
+        tr.sync.check()
+        res[f"loss_dp_{overlap}_{comm}"] = tr.reduced_loss()
+        res[f"tokens_{overlap}_{comm}"] = tr.num_input_tokens_seen
         del tr, m
     m1, _ = _mk_lm(cfg_o, 11, 2 * world, 96, device=dev)
     one = m1.forward_backward(full, labels, num_items_in_batch=float((labels != -100).sum()))
@@ -362,7 +371,7 @@ def test_data_parallel_path_on_two_gpus(tmp_path):
     mp.spawn(_dp_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     r = json.load(open(tmp_path / "res.json"))
     print("2-GPU data-parallel check:", r)
-    for ov in ("False", "True"):
-        assert abs(r[f"loss_dp_{ov}"] - r["loss_single"]) < 2e-4 * abs(r["loss_single"]), r
-        assert r[f"tokens_{ov}"] == r["tokens_False"]
+    for key in ("False_nccl", "True_nccl", "False_p2p", "True_p2p"):
+        assert abs(r[f"loss_dp_{key}"] - r["loss_single"]) < 2e-4 * abs(r["loss_single"]), r
+        assert r[f"tokens_{key}"] == r["tokens_False_nccl"]
     assert r["grad_err_vs_single"] < 1e-2 and r["dpo_ranks_identical"]

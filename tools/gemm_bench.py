@@ -32,7 +32,10 @@ shapes = [  # (name, M, N, K, a_mn, b_mn)
     ("qkv_dgrad", M, 896, 1152, 0, 1), ("o_dgrad", M, 896, 896, 0, 1), ("o_wgrad", 896, 896, M, 1, 1),
     ("head_dgrad", M, 896, 512, 0, 1), ("head_wgrad", 512, 896, M, 1, 1),
 ]
+_only = os.environ.get('GEMM_SHAPES')
 for name, m, n, k, a_mn, b_mn in shapes:
+    if _only and name not in _only.split(','):
+        continue
     a = torch.randn((k, m) if a_mn else (m, k), device=dev).to(torch.bfloat16)
     b = torch.randn((k, n) if b_mn else (n, k), device=dev).to(torch.bfloat16)
     out = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
@@ -41,7 +44,7 @@ for name, m, n, k, a_mn, b_mn in shapes:
     for bn in (0, 128, 256):
         t = timeit(lambda: ops.gemm(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), out=out, force_bn=bn))
         res.append(f"bn{bn}: {flops / t / 1e9:7.1f} TF/s ({t * 1e3:7.1f} us)")
-    for bn in (0,):   # with the scratch buffer: stream-K balancing
+    for bn in (0, 256):   # with the scratch buffer: stream-K balancing
         t = timeit(lambda: ops.gemm(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), out=out, force_bn=bn, streamk=True))
         res.append(f"sk{bn}: {flops / t / 1e9:7.1f} TF/s ({t * 1e3:7.1f} us)")
     A = a.t() if a_mn else a
