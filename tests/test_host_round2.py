@@ -52,7 +52,10 @@ model = types.SimpleNamespace(config=types.SimpleNamespace(n_layers=nl), tensors
                               device=torch.device("cpu"))
 sync = GradSync(model, layers_per_bucket=2, overlap=True)      # overlap silently off: CPU gradients
 assert sync.world == 2 and not sync.overlap
+assert sync.backend == "nccl" and sync.p2p is None             # host gradients: torch.distributed (here gloo), never the peer kernel
+assert len(sync.buckets) == 3                                  # layers (3,4), (1,2), (0)
 sync.reduce()
+sync.check()
 ref = grads.clone(); dist.all_reduce(ref)
 assert torch.equal(model.grads, ref), float((model.grads - ref).abs().max())     # bucketed == one big all-reduce, bit for bit
 tot = HostReducer().sum([3 + rank, 10.0])
@@ -70,6 +73,25 @@ def test_gradsync_buckets_and_host_reducer_gloo_world2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29641", str(script)],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SYNC_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_peer_allreduce_range_rule_and_default_bucket_size():
+    """The peer-memory kernel moves 16-byte chunks: ranges must start and end on multiples of 8 bf16 elements (anything else
+    goes through torch.distributed); it uses 2-layer buckets, NCCL keeps 4."""
+    from slamkit_b200.p2p import MAX_SLOTS, MAX_WORLD, PeerAllReduce
+    assert PeerAllReduce.supports(0, 8) and PeerAllReduce.supports(64, 64 + 896 * 8)
+    assert not PeerAllReduce.supports(4, 12) and not PeerAllReduce.supports(0, 7) and not PeerAllReduce.supports(8, 8)
+    assert MAX_WORLD == 8 and MAX_SLOTS >= 64
+    from slamkit_b200.lm import LMConfig
+    # every tensor of the LM layout starts on a 64-element boundary, so every bucket of the real model qualifies
+    import types
+    from slamkit_b200.trainer import plan_buckets
+    cfg = LMConfig()
+    per_layer = 896 + 1152 * 896 + 1152 + 896 * 896 + 896 + 9728 * 896 + 896 * 4864
+    pad = lambda n: (n + 63) // 64 * 64
+    starts = [l * pad(per_layer) for l in range(cfg.n_layers + 1)]
+    buckets, tail = plan_buckets(starts, starts[-1] + 896 + 512 * 896, 2)
+    assert len(buckets) == 12 and all(PeerAllReduce.supports(lo, hi) for _, lo, hi in buckets) and PeerAllReduce.supports(*tail)
 
 
 # ------------------------------------------------------------------------------------------------ token counting
