@@ -342,8 +342,49 @@ class B200UnitLM:
         ll = tok.sum(-1)
         return ll / mask.sum(-1) if mean_nll else ll
 
-    def generate(self, *a, **k):
-        raise NotImplementedError("generation (KV-cache decode) is outside the B200 hot path (SURVEY.md §2 row 3)")
+    @torch.inference_mode()
+    def generate(self, inputs: Optional[torch.Tensor] = None, generation_config=None, **kwargs) -> torch.Tensor:
+        """TokenLM.generate (slamkit/model/token_lm.py:19-27; UnitLM.generate -> HF GenerationMixin, unit_lm.py:196-198):
+        greedy or sampled continuation of left-padded prompts with HF's logits processing (generation.py).  No KV cache --
+        decoding is not a hot path here -- so every new token re-runs the forward kernels on one sequence's prefix."""
+        from .generation import generate_tokens
+        if inputs is None:
+            inputs = kwargs.pop("input_ids", None)
+        if inputs is None:
+            raise ValueError("generate: no prompt (inputs / input_ids)")
+        keys = ("max_new_tokens", "max_length", "do_sample", "temperature", "top_k", "top_p", "eos_token_id", "pad_token_id",
+                "bad_words_ids")
+        opts = {}
+        if generation_config is not None:
+            for k in keys:
+                v = getattr(generation_config, k, None)
+                if v is not None:
+                    opts[k] = v
+            if "max_new_tokens" in opts:
+                opts.pop("max_length", None)
+        for k in keys:
+            if kwargs.get(k) is not None:
+                opts[k] = kwargs[k]
+                if k == "max_new_tokens":
+                    opts.pop("max_length", None)
+        attention_mask = kwargs.get("attention_mask")
+        ignored = {"attention_mask", "token_type_ids", "use_cache", "return_dict_in_generate", "output_scores", "synced_gpus"}
+        unknown = sorted(k for k in kwargs if k not in keys and k not in ignored and kwargs[k] is not None)
+        if unknown:
+            raise NotImplementedError(f"generate: unsupported arguments {unknown} (greedy / sampling with temperature, top_k, "
+                                      "top_p, bad_words_ids, eos / pad ids and length limits are implemented)")
+        opts.setdefault("eos_token_id", getattr(self.config, "eos_token_id", 1))      # UnitTokeniser: bos = eos = 1
+        opts.setdefault("pad_token_id", self.config.pad_token_id)
+        if opts.get("do_sample") and "top_k" not in opts:
+            opts["top_k"] = 50                                    # transformers' GenerationConfig default
+        V = self.config.vocab_size
+
+        def next_logits(ids: torch.Tensor) -> torch.Tensor:
+            if ids.shape[1] > self.max_seq:
+                raise L.SkError(f"generate: sequence of {ids.shape[1]} tokens exceeds the bound workspace (max_seq = {self.max_seq})")
+            return self.forward(ids).logits[0, -1, :V].float().cpu()
+
+        return generate_tokens(next_logits, inputs, attention_mask=attention_mask, max_positions=self.config.max_positions, **opts)
 
 
 class B200AdamW:

@@ -269,6 +269,42 @@ def test_cli_train_resume_is_bit_identical(tmp_path):
         train.main(common + ["cont_training=true", f"training_args.output_dir={tmp_path}/empty"])
 
 
+def test_generate_on_the_cuda_path_follows_the_oracle():
+    """`TokenLM.generate` (slamkit/model/token_lm.py:19-27) through the forward kernels: greedy continuation of a LEFT-padded
+    batch (SpeechLM.generate's calling convention) -- every chosen token is the oracle's argmax for that prefix (up to bf16
+    near-ties), the padded prompt is returned in front, `bad_words_ids` / eos / sampling arguments are honoured, and the
+    nn.Module face forwards to the same code.  (The selection rules themselves are checked against transformers' own
+    `generate` on CPU: tests/test_generation_cpu.py.)"""
+    from oracle import lm_oracle as O
+    from slamkit_b200.hf_module import B200UnitLMModule
+    cfg_o = _tiny_o()
+    m, p = _mk_lm(cfg_o, 5, 2, 64)
+    g = torch.Generator().manual_seed(2)
+    a, b = torch.randint(2, 502, (9,), generator=g), torch.randint(2, 502, (5,), generator=g)
+    ids, mask = torch.zeros(2, 9, dtype=torch.long), torch.zeros(2, 9, dtype=torch.long)
+    ids[0], mask[0] = a, 1
+    ids[1, 4:], mask[1, 4:] = b, 1
+    out = m.generate(ids, attention_mask=mask, max_new_tokens=6, do_sample=False, eos_token_id=None)
+    assert out.shape == (2, 15) and torch.equal(out[:, :9], ids)
+    torch.set_num_threads(_usable_cpus())
+    for r, prompt in enumerate((a, b)):
+        seq = prompt.tolist()
+        for tok in out[r, 9:].tolist():
+            lo = O.forward_logits(p, cfg_o, torch.tensor([seq]))[0, -1].float()
+            assert float(lo[tok]) >= float(lo.max()) - 0.02 * float(lo.max() - lo.min()), (r, len(seq), tok, int(lo.argmax()))
+            seq.append(tok)
+    first = int(out[0, 9])
+    out2 = m.generate(ids, attention_mask=mask, max_new_tokens=3, bad_words_ids=[[first]], eos_token_id=None)
+    assert first not in out2[0, 9:].tolist()
+    out3 = m.generate(ids, attention_mask=mask, max_new_tokens=4, eos_token_id=first)      # row 0 stops at once, tail = pad id
+    assert int(out3[0, 9]) == first and out3[0, 10:].tolist() == [m.config.pad_token_id] * (out3.shape[1] - 10)
+    torch.manual_seed(0)
+    out4 = B200UnitLMModule(m).generate(ids, attention_mask=mask, max_new_tokens=5, do_sample=True, temperature=0.8, top_k=25)
+    assert out4.shape[0] == 2 and 9 < out4.shape[1] <= 14 and int(out4[:, 9:].max()) < 502
+    with pytest.raises(NotImplementedError):
+        m.generate(ids, attention_mask=mask, num_beams=4)
+
+
 # ---------------------------------------------------------------------------------------------- >= 2 GPUs
 def _free_port():
     s = socket.socket()
