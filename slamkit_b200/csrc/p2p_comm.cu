@@ -39,7 +39,7 @@ namespace {
 constexpr int P2P_MAX_WORLD = 8;
 constexpr int P2P_SLOTS = 256;                       // buckets per reduction (flag rows)
 constexpr int P2P_THREADS = 128;                     // 4 warps: one per SM sub-partition
-constexpr uint64_t SK_P2P_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+constexpr uint64_t SK_P2P_TIMEOUT_NS = 60ull * 1000 * 1000 * 1000;   // a dead peer, not a slow one: ranks may be seconds apart at start-up
 
 // flag array of one rank (uint32): READY[P2P_SLOTS][8] | DONE[P2P_SLOTS][8] | CTA counters[P2P_SLOTS]
 constexpr size_t P2P_FLAG_WORDS = 2 * P2P_SLOTS * P2P_MAX_WORLD + P2P_SLOTS;
