@@ -53,15 +53,23 @@ class PeerAllReduce:
         self.device = buf.device
         self.epoch = 0
         with torch.cuda.device(self.device):
-            if self.device.index not in _FLAGS:
-                own = C.c_void_p()
-                L.check(self.lib.sk_p2p_alloc(C.c_int64(int(self.lib.sk_p2p_flag_bytes())), C.byref(own)))
-                _FLAGS[self.device.index] = int(own.value)
-            self._flags_own = C.c_void_p(_FLAGS[self.device.index])
-            mine = {"host": socket.gethostname(), "pid": os.getpid(), "dev": self.device.index, "n": buf.numel(),
-                    "buf": self._export(buf.data_ptr()), "flags": self._export(self._flags_own.value)}
+            # a rank that cannot export its memory still takes part in the exchange (with the reason), so that every rank
+            # reaches the same verdict instead of waiting for it in a collective
+            try:
+                if self.device.index not in _FLAGS:
+                    own = C.c_void_p()
+                    L.check(self.lib.sk_p2p_alloc(C.c_int64(int(self.lib.sk_p2p_flag_bytes())), C.byref(own)))
+                    _FLAGS[self.device.index] = int(own.value)
+                self._flags_own = C.c_void_p(_FLAGS[self.device.index])
+                mine = {"host": socket.gethostname(), "pid": os.getpid(), "dev": self.device.index, "n": buf.numel(),
+                        "buf": self._export(buf.data_ptr()), "flags": self._export(self._flags_own.value)}
+            except L.SkError as e:
+                mine = {"error": f"rank {self.rank}: {e}"}
             infos: List[Optional[dict]] = [None] * self.world
             dist.all_gather_object(infos, mine, group=group)
+            failed = [i["error"] for i in infos if "error" in i]
+            if failed:
+                raise L.SkError("peer all-reduce: " + "; ".join(failed))
             if len({i["host"] for i in infos}) != 1:
                 raise L.SkError("peer all-reduce: ranks span several hosts")
             if len({i["n"] for i in infos}) != 1:
