@@ -3,7 +3,8 @@
 
 Default workload (BASELINE.json configs[1]): one optimiser step of the SLAM pre-training recipe -- Qwen2.5-0.5B-shaped
 unit LM (358 M params, vocab 502, bf16 params and optimiser state), per-GPU micro-batch [8, 1024] synthetic unit
-tokens, gradient clip 0.5 + AdamW -- data-parallel over N GPUs with one NCCL gradient all-reduce per step.
+tokens, gradient clip 0.5 + AdamW -- data-parallel over N GPUs with one gradient all-reduce per step (the package's
+peer-memory kernel on one node; `config.dp_comm` in the JSON line says which backend ran).
 
   python bench.py --gpus N --steps K --warmup W            # our arm (one JSON line on rank 0)
   python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference's algorithm on the host cores

@@ -187,7 +187,8 @@ int sk_lm_forward_backward(SkLm* lm, const int64_t* ids, const int64_t* labels, 
                            float num_items, float dloss, int accumulate, float* stats, void* stream);
 /* Data-parallel overlap hook: n = n_layers+1 caller-owned cudaEvent_t handles; during sk_lm_forward_backward event l is
  * recorded on the compute stream once layer l's gradients are final (event n_layers: final-norm part), so the host can
- * enqueue that bucket's NCCL all-reduce on a side stream while the backward pass continues.  NULL/0 disables. */
+ * enqueue that bucket's all-reduce (sk_p2p_* below, or NCCL) on a side stream while the backward pass continues.
+ * NULL/0 disables. */
 int sk_lm_set_backward_events(SkLm* lm, void* const* events, int n);
 /* Preference optimisation (DPO, cli/preference_alignment_train.py -> trl.DPOTrainer): the loss is not a
  * plain CE, but its logit gradient is a per-SEQUENCE-weighted CE gradient.  sk_lm_forward_rows runs the forward pass

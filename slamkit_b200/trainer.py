@@ -3,10 +3,12 @@
 Replaces what HF Trainer + accelerate's DDP wrapper do around `training_step` (HF:trainer.py:1867-2014;
 config/training_args/default.yaml:18 `ddp_find_unused_parameters: false`) and `SLAMTrainer.training_step`
 (slamkit/trainer/slam_trainer.py:59-71): one process per GPU, each rank computes gradients normalised by the GLOBAL
-number of label tokens, then a SUM all-reduce over NVLink (NCCL via torch.distributed -- the only collective on the data
-path) and the optimiser step.  The flat bf16 gradient buffer is reduced in a few large buckets; bucket k's all-reduce is
-enqueued on a side stream as soon as the backward pass has finished the layers it covers (CUDA events recorded inside
-`sk_lm_forward_backward`), so communication overlaps the rest of the backward pass.
+number of label tokens, then a SUM all-reduce of the flat bf16 gradient buffer over NVLink and the optimiser step.  The
+buffer is reduced in buckets; bucket k's reduction is enqueued on a side stream as soon as the backward pass has finished
+the layers it covers (CUDA events recorded inside `sk_lm_forward_backward`), so communication overlaps the rest of the
+backward pass.  Ranks that share a node reduce with our own kernel over CUDA-IPC peer memory (`p2p.PeerAllReduce`,
+csrc/p2p_comm.cu: small-footprint CTAs that co-reside with the backward kernels, rank-order fp32 sums, bit-identical on
+every rank); across nodes, or when a peer cannot be mapped, the same buckets go through `torch.distributed.all_reduce`.
 
 Host-side scalars (token counts) never touch the GPU: labels are counted where the collator produced them (host memory)
 and summed over ranks through a gloo group, so no step of the loop waits for the device.
